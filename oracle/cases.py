@@ -1,0 +1,172 @@
+"""Seeded synthetic inputs shared by the golden-vector generator, the tests and bench.py.
+
+Everything is drawn from ``numpy.random.default_rng(seed)`` (PCG64: bit-identical on
+every machine), so the GPU box regenerates exactly the inputs the reference saw in
+the build container.  Test infrastructure (see oracle/tt_oracle.py header).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def random_tt(shape, ranks, seed, dtype=np.float64):
+    """Random TT cores [r_{k-1}, I_k, r_k] with N(0,1) entries (like tn.randn, create.py:210-357)."""
+    rng = _rng(seed)
+    N = len(shape)
+    if not hasattr(ranks, "__len__"):
+        ranks = [ranks] * (N - 1)
+    rs = [1] + list(ranks) + [1]
+    return [rng.standard_normal((rs[k], shape[k], rs[k + 1])).astype(dtype) for k in range(N)]
+
+
+def tt_full(cores, dtype=None):
+    f = np.ones((1, 1), dtype=cores[0].dtype)
+    shape = []
+    for c in cores:
+        shape.append(c.shape[1])
+        f = (f @ c.reshape(c.shape[0], -1)).reshape(-1, c.shape[2])
+    out = f[:, 0].reshape(shape)
+    return out if dtype is None else out.astype(dtype)
+
+
+def analytic_field_128():
+    """docs/tutorials/decompositions.ipynb:37 — the analytic 128^3 fp64 field."""
+    X, Y, Z = np.meshgrid(range(128), range(128), range(128))
+    return np.sqrt(np.sqrt(X) * (Y + Z) + Y * Z**2) * (X + np.sin(Y) * np.cos(Z))
+
+
+def make_dense(spec):
+    kind = spec["kind"]
+    dtype = np.dtype(spec.get("dtype", "float32"))
+    if kind == "randn":
+        return _rng(spec["seed"]).standard_normal(spec["shape"]).astype(dtype)
+    if kind == "tt_noise":  # structured twin: low TT-rank signal + relative Gaussian noise
+        cores = random_tt(spec["shape"], spec["rank"], spec["seed"], np.float64)
+        X = tt_full(cores)
+        noise = _rng(spec["seed"] + 1).standard_normal(X.shape)
+        X = X + spec["noise"] * X.std() * noise
+        return X.astype(dtype)
+    if kind == "analytic128":
+        return analytic_field_128().astype(dtype)
+    if kind == "smooth":  # fast-decaying singular spectrum
+        grids = np.meshgrid(*[np.linspace(0, 1, s) for s in spec["shape"]], indexing="ij")
+        X = 1.0 / (1.0 + sum((i + 1) * g for i, g in enumerate(grids)))
+        return X.astype(dtype)
+    if kind == "zeros":
+        return np.zeros(spec["shape"], dtype)
+    raise ValueError(kind)
+
+
+def make_tt(spec):
+    dtype = np.dtype(spec.get("dtype", "float64"))
+    cores = random_tt(spec["shape"], spec["rank"], spec["seed"], dtype)
+    if spec.get("doubled"):  # t + t : rank-doubling block cores (tensor.py:445-520 semantics)
+        out = []
+        N = len(cores)
+        for k, c in enumerate(cores):
+            r0, I, r1 = c.shape
+            if k == 0:
+                out.append(np.concatenate([c, c], axis=2))
+            elif k == N - 1:
+                out.append(np.concatenate([c, c], axis=0))
+            else:
+                z = np.zeros((2 * r0, I, 2 * r1), dtype)
+                z[:r0, :, :r1] = c
+                z[r0:, :, r1:] = c
+                out.append(z)
+        cores = out
+    return cores
+
+
+def make_matrix(spec):
+    dtype = np.dtype(spec.get("dtype", "float64"))
+    rng = _rng(spec["seed"])
+    m, n = spec["shape"]
+    if spec.get("lowrank"):
+        k = spec["lowrank"]
+        M = rng.standard_normal((m, k)) @ rng.standard_normal((k, n))
+        M = M + spec.get("noise", 0.0) * rng.standard_normal((m, n))
+    elif spec.get("zero"):
+        M = np.zeros((m, n))
+    else:
+        M = rng.standard_normal((m, n))
+    return M.astype(dtype)
+
+
+def make_cp_dense(spec):
+    rng = _rng(spec["seed"])
+    dtype = np.dtype(spec.get("dtype", "float64"))
+    fac = [rng.standard_normal((s, spec["Rtrue"])) for s in spec["shape"]]
+    letters = "abcdefgh"[: len(fac)]
+    X = np.einsum(",".join(f"{l}r" for l in letters) + "->" + letters, *fac)
+    X = X + spec.get("noise", 0.0) * X.std() * rng.standard_normal(X.shape)
+    return X.astype(dtype)
+
+
+# ---- dense TT-SVD cases (tn.Tensor(X, ranks_tt=/eps=)) ------------------------------
+TTSVD_CASES = {
+    # BASELINE.json configs[0]
+    "cfg1_randn16x4_f32": dict(kind="randn", shape=(16, 16, 16, 16), seed=0, dtype="float32", ranks_tt=4),
+    "cfg1_randn16x4_f64": dict(kind="randn", shape=(16, 16, 16, 16), seed=0, dtype="float64", ranks_tt=4),
+    # tests/test_gpu.py:9-27 precedent
+    "gpu_randn16x3_r3": dict(kind="randn", shape=(16, 16, 16), seed=1, dtype="float32", ranks_tt=3),
+    # ragged shapes, ranks list, rank larger than feasible
+    "ragged_f32": dict(kind="randn", shape=(7, 12, 5, 9, 6), seed=2, dtype="float32", ranks_tt=[3, 8, 6, 2]),
+    "ragged_f64_bigrank": dict(kind="randn", shape=(4, 6, 5, 3), seed=3, dtype="float64", ranks_tt=50),
+    "two_modes": dict(kind="randn", shape=(40, 30), seed=4, dtype="float64", ranks_tt=5),
+    # structured twins (meaningful error)
+    "twin_small_f32": dict(kind="tt_noise", shape=(12, 10, 8, 9, 7), rank=4, noise=1e-2, seed=5, dtype="float32", ranks_tt=4),
+    "twin_small_f64": dict(kind="tt_noise", shape=(12, 10, 8, 9, 7), rank=4, noise=1e-3, seed=5, dtype="float64", ranks_tt=4),
+    "twin_16x5_f32": dict(kind="tt_noise", shape=(16,) * 5, rank=8, noise=1e-2, seed=6, dtype="float32", ranks_tt=8),
+    # eps-driven
+    "eps_twin_f64": dict(kind="tt_noise", shape=(12, 10, 8, 9, 7), rank=4, noise=1e-6, seed=7, dtype="float64", eps=1e-4),
+    "eps_smooth_f64": dict(kind="smooth", shape=(20, 18, 16, 14), dtype="float64", eps=1e-6),
+    "smooth_f32_r6": dict(kind="smooth", shape=(20, 18, 16, 14), dtype="float32", ranks_tt=6),
+    # tutorial known answers (docs/tutorials/decompositions.ipynb:68,361)
+    "analytic128_r3": dict(kind="analytic128", dtype="float64", ranks_tt=3, big=False),
+    "analytic128_eps": dict(kind="analytic128", dtype="float64", eps=1e-5, big=False),
+    # medium: same character as BASELINE configs[1] (random Gaussian, r=32) at a CPU-feasible size
+    "randn32x5_r32_f32": dict(kind="randn", shape=(32,) * 5, seed=8, dtype="float32", ranks_tt=32, big=True),
+    "twin32x5_r32_f32": dict(kind="tt_noise", shape=(32,) * 5, rank=32, noise=1e-2, seed=9, dtype="float32", ranks_tt=32, big=True),
+    "randn64x4_r32_f32": dict(kind="randn", shape=(64,) * 4, seed=10, dtype="float32", ranks_tt=32, big=True),
+    "zeros": dict(kind="zeros", shape=(6, 5, 4), dtype="float64", ranks_tt=3),
+}
+
+# ---- round_tt on TT input ----------------------------------------------------------
+ROUND_CASES = {
+    "rmax_8to3_f64": dict(shape=(16,) * 5, rank=8, seed=20, dtype="float64", rmax=3),
+    "rmax_list_f64": dict(shape=(9, 8, 7, 6, 5, 4), rank=6, seed=21, dtype="float64", rmax=[2, 4, 5, 3, 2]),
+    "doubled_eps_f64": dict(shape=(8,) * 6, rank=5, seed=22, dtype="float64", doubled=True, eps=1e-8),
+    "doubled_eps_f32": dict(shape=(8,) * 6, rank=5, seed=22, dtype="float32", doubled=True, eps=1e-4),
+    "cfg3_small_f64": dict(shape=(32,) * 6, rank=16, seed=23, dtype="float64", rmax=4),
+    "eps_only_f64": dict(shape=(10,) * 5, rank=7, seed=24, dtype="float64", eps=0.3),
+}
+
+# ---- truncated_svd ------------------------------------------------------------------
+TSVD_CASES = {
+    "rand_32x32_eps": dict(shape=(32, 32), seed=30, eps=0.3),
+    "wide_16x200_rmax": dict(shape=(16, 200), seed=31, rmax=5),
+    "tall_300x12_delta": dict(shape=(300, 12), seed=32, delta=2.0),
+    "lowrank_60x80": dict(shape=(60, 80), seed=33, lowrank=6, noise=1e-9, eps=1e-6),
+    "zero_10x7": dict(shape=(10, 7), seed=34, zero=True, rmax=3),
+    "f32_64x128_rmax": dict(shape=(64, 128), seed=35, rmax=16, dtype="float32"),
+}
+
+# ---- maxvol ---------------------------------------------------------------------------
+MAXVOL_CASES = {
+    "cfg5_320x10": dict(shape=(320, 10), seed=40),
+    "tall_1000x20": dict(shape=(1000, 20), seed=41),
+    "square_8x8": dict(shape=(8, 8), seed=42),
+    "wide_5x7": dict(shape=(5, 7), seed=43),
+    "small_64x8": dict(shape=(64, 8), seed=44),
+}
+
+# ---- CP-ALS (fp64 oracle, fixed sweep count: SURVEY §0.5) -------------------------------
+CP_CASES = {
+    "cp_16x4_R5": dict(shape=(16,) * 4, Rtrue=5, R=5, sweeps=10, noise=1e-2, seed=50, dtype="float64"),
+    "cp_20x3_R8": dict(shape=(20, 18, 16), Rtrue=8, R=8, sweeps=8, noise=1e-3, seed=51, dtype="float64"),
+}

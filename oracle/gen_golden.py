@@ -1,0 +1,136 @@
+"""Generate golden vectors from the REAL reference (rballester/tntorch @ /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    cd /tmp && python /root/repo/oracle/gen_golden.py
+
+Writes ``tests/golden/*.npz``.  Inputs are produced by ``oracle/cases.py`` (NumPy
+``default_rng`` streams, bit-identical on every machine), so tests regenerate the
+inputs and only the reference's outputs (ranks, relative errors, singular values,
+small reconstructions, maxvol index sets) are stored.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+import tntorch as tn  # noqa: E402  (the real reference)
+from tntorch.maxvol import py_maxvol as ref_maxvol  # noqa: E402
+
+from oracle import cases  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(os.cpu_count())
+
+
+def rel_err64(X, t):
+    X64 = torch.as_tensor(X, dtype=torch.float64)
+    return float(torch.norm(X64 - t.torch().double()) / torch.norm(X64))
+
+
+def gen_ttsvd():
+    out = {}
+    for name, spec in cases.TTSVD_CASES.items():
+        X = cases.make_dense(spec)
+        for alg in ("svd", "eig"):
+            if spec.get("big") and alg == "svd":
+                continue
+            kw = dict(algorithm=alg)
+            if spec.get("eps") is not None:
+                kw["eps"] = spec["eps"]
+            else:
+                kw["ranks_tt"] = spec["ranks_tt"]
+            # the reference's zero-matrix branch (round.py:137-145) allocates in the DEFAULT dtype
+            torch.set_default_dtype(torch.float64 if X.dtype == np.float64 else torch.float32)
+            t = tn.Tensor(torch.as_tensor(X), **kw)
+            torch.set_default_dtype(torch.float32)
+            out[f"{name}/{alg}/ranks"] = np.asarray(t.ranks_tt, dtype=np.int64)
+            out[f"{name}/{alg}/relerr"] = np.float64(rel_err64(X, t))
+            if X.size <= 70000:
+                out[f"{name}/{alg}/recon"] = t.torch().double().numpy()
+            print(name, alg, list(t.ranks_tt), out[f"{name}/{alg}/relerr"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "ttsvd.npz"), **out)
+
+
+def gen_round():
+    out = {}
+    for name, spec in cases.ROUND_CASES.items():
+        cores = cases.make_tt(spec)
+        dense = cases.tt_full(cores)
+        for alg in ("svd", "eig"):
+            t = tn.Tensor([torch.as_tensor(c.copy()) for c in cores])
+            kw = dict(algorithm=alg)
+            if "eps" in spec:
+                kw["eps"] = spec["eps"]
+            if "rmax" in spec:
+                kw["rmax"] = spec["rmax"]
+            t.round_tt(**kw)
+            out[f"{name}/{alg}/ranks"] = np.asarray(t.ranks_tt, dtype=np.int64)
+            out[f"{name}/{alg}/relerr"] = np.float64(rel_err64(dense, t))
+            print(name, alg, list(t.ranks_tt), out[f"{name}/{alg}/relerr"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "round_tt.npz"), **out)
+
+
+def gen_truncsvd():
+    out = {}
+    for name, spec in cases.TSVD_CASES.items():
+        M = cases.make_matrix(spec)
+        for alg in ("svd", "eig"):
+            for lo in (True, False):
+                kw = {k: spec[k] for k in ("eps", "delta", "rmax") if k in spec}
+                left, right = tn.truncated_svd(torch.as_tensor(M), left_ortho=lo, algorithm=alg, **kw)
+                key = f"{name}/{alg}/{'L' if lo else 'R'}"
+                out[key + "/rank"] = np.int64(left.shape[1])
+                out[key + "/prod"] = (left @ right).double().numpy()
+                out[key + "/orth"] = np.float64(
+                    float(torch.dist(left.T @ left, torch.eye(left.shape[1], dtype=left.dtype)))
+                    if lo
+                    else float(torch.dist(right @ right.T, torch.eye(left.shape[1], dtype=left.dtype)))
+                )
+                print(key, int(left.shape[1]), flush=True)
+    np.savez_compressed(os.path.join(OUT, "truncated_svd.npz"), **out)
+
+
+def gen_maxvol():
+    out = {}
+    for name, spec in cases.MAXVOL_CASES.items():
+        A = cases.make_matrix(spec)
+        idx, C = ref_maxvol(A)
+        out[f"{name}/index"] = np.asarray(idx, dtype=np.int64)
+        out[f"{name}/absmax"] = np.float64(np.abs(C).max())
+        print(name, idx[:6], np.abs(C).max(), flush=True)
+    np.savez_compressed(os.path.join(OUT, "maxvol.npz"), **out)
+
+
+def gen_cpals():
+    out = {}
+    for name, spec in cases.CP_CASES.items():
+        X = cases.make_cp_dense(spec)
+        torch.manual_seed(0)
+        t = tn.Tensor(torch.as_tensor(X), ranks_cp=spec["R"], max_iter=spec["sweeps"], tol=float("-inf"))
+        out[f"{name}/relerr"] = np.float64(rel_err64(X, t))
+        print(name, out[f"{name}/relerr"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "cp_als.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp"]
+    if "ttsvd" in which:
+        gen_ttsvd()
+    if "round" in which:
+        gen_round()
+    if "tsvd" in which:
+        gen_truncsvd()
+    if "maxvol" in which:
+        gen_maxvol()
+    if "cp" in which:
+        gen_cpals()
