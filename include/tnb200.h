@@ -1,0 +1,142 @@
+/*
+ * tnb200 — B200-native (sm_100a) decomposition / rounding hot path for tntorch.
+ *
+ * C-ABI drop-in boundary.  The reference (rballester/tntorch) is 100 % Python and has no
+ * FFI of its own; these entry points are what a ctypes binding added to the
+ * reference would call in place of its torch.linalg call sites.  Each declaration cites the
+ * reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - all matrix / tensor arguments are DEVICE pointers unless the name ends in `_host`;
+ *     dense tensors are C-contiguous (row-major), exactly torch's default layout;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, and a call returns
+ *     after at most the host synchronisations needed to report data-dependent ranks
+ *     (the reference itself syncs once per round_tt: tensor.py:2051 `.item()`);
+ *   - the library owns no device memory: workspaces are sized by the *_workspace_bytes
+ *     queries and allocated by the caller (torch's caching allocator in the Python shim);
+ *   - return value 0 = ok; non-zero = error code below, text via tnb_last_error();
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TNB200_H
+#define TNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNB_OK 0
+#define TNB_ERR_INVALID 1      /* bad argument (maps to ValueError / AssertionError in the shim) */
+#define TNB_ERR_CUDA 2         /* CUDA runtime / driver error                                     */
+#define TNB_ERR_WORKSPACE 3    /* workspace or output buffer too small                            */
+#define TNB_ERR_UNSUPPORTED 4  /* shape/mode outside what the kernels cover (raised, never faked) */
+#define TNB_ERR_NOCONV 5       /* iterative eigensolver did not converge                          */
+
+#define TNB_F32 0
+#define TNB_F64 1
+
+/* flags for tnb_ttsvd / tnb_tt_round */
+#define TNB_FLAG_NO_TENSORCORE 1u /* force the generic fp32/fp64 CUDA-core kernels (debug / parity A-B) */
+#define TNB_FLAG_BATCH_MODE 2u    /* reference `batch=True` rank rule: rank = min(rmax, len(S)), no eps  */
+
+int tnb_version(void);
+const char* tnb_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py `gpu_launches`) */
+uint64_t tnb_launch_count(void);
+/* 1 if the tcgen05/TMA kernels are usable on the current device (sm_100), else 0 */
+int tnb_has_tensorcore_path(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense tensor -> TT cores (TT-SVD).
+ * Replaces: tn.Tensor(data, ranks_tt=...)  tensor.py:401-408  (= _full_rank_tt tensor.py:10-104
+ *           + Tensor.round_tt tensor.py:2008-2083 + tn.truncated_svd round.py:52-187).
+ *   dtype      TNB_F32 / TNB_F64 (cores come back in the same dtype, like the reference)
+ *   data       dense tensor, shape[0..ndim), C-contiguous
+ *   rmax       ndim-1 entries, <=0 meaning "no cap" (reference: rmax=None)
+ *   eps        relative error budget of round_tt (reference default 1e-14)
+ *   cores      output buffer; core k is written at element offset core_offsets_host[k] with shape
+ *              [ranks_host[k], shape[k], ranks_host[k+1]]; capacity from tnb_ttsvd_cores_capacity()
+ *   ranks_host ndim+1 ints (host), ranks_host[0] = ranks_host[ndim] = 1
+ *   info_host  optional (may be NULL) 8 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix
+ *              products, [3]=#tensor-core Gram launches, [4..7] reserved
+ * ------------------------------------------------------------------------------------------ */
+int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host);
+size_t tnb_ttsvd_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* rmax, uint32_t flags);
+int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
+              uint32_t flags, void* workspace, size_t workspace_bytes, void* cores, int64_t cores_capacity,
+              int32_t* ranks_host, double* info_host, void* stream);
+
+/* Same, but `data_host` / `cores_host` are HOST buffers (pinned for full speed): the H2D copy is
+ * chunked and overlapped with the first Gram pass, cores are copied back before returning.
+ * `device_buffer` must hold the dense tensor (prod(shape) elements) and is left filled. */
+int tnb_ttsvd_host(int dtype, const void* data_host, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
+                   uint32_t flags, void* device_buffer, void* workspace, size_t workspace_bytes, void* cores_dev,
+                   int64_t cores_capacity, void* cores_host, int32_t* ranks_host, double* info_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TT rounding of an existing tensor train.
+ * Replaces: Tensor.round_tt(eps, rmax)  tensor.py:2008-2083 (phase A: orthogonalize tensor.py:1881-1909
+ *           -> left_orthogonalize tensor.py:1800-1833; phase B: truncated_svd round.py:52-187).
+ *   cores_in   ndim device pointers (host array of pointers), core k has shape [ranks_in[k], shape[k], ranks_in[k+1]]
+ *   cores_out / ranks_host / capacity: as for tnb_ttsvd, with capacity from tnb_tt_round_cores_capacity()
+ * ------------------------------------------------------------------------------------------ */
+int64_t tnb_tt_round_cores_capacity(int ndim, const int64_t* shape, const int32_t* ranks_in, const int32_t* rmax,
+                                    int64_t* core_offsets_host);
+size_t tnb_tt_round_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                    const int32_t* rmax);
+int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                 const int32_t* rmax, double eps, uint32_t flags, void* workspace, size_t workspace_bytes,
+                 void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Two-factor rank-revealing split  M (m x n)  ->  left (m x r), right (r x n).
+ * Replaces: tn.truncated_svd(M, delta, eps, rmax, left_ortho)  round.py:52-187.
+ *   delta < 0 means "not given"; eps < 0 means "not given"; both given -> TNB_ERR_INVALID
+ *   (round.py:77-78 ValueError).  rmax <= 0 means no cap.  left/right need m*min(m,n) and
+ *   min(m,n)*n elements of capacity; *rank_host receives r.
+ * ------------------------------------------------------------------------------------------ */
+size_t tnb_truncated_svd_workspace_bytes(int dtype, int64_t m, int64_t n);
+int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double delta, double eps, int32_t rmax,
+                      int left_ortho, void* workspace, size_t workspace_bytes, void* left, void* right,
+                      int32_t* rank_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks (exposed for tests, profiling and the Python shim).
+ * ------------------------------------------------------------------------------------------ */
+/* G (n x n, fp64) = A^T A for A (rows x n), dtype f32/f64; fp64 accumulation on CUDA cores.
+ * Replaces: `M.permute(dims) @ M` round.py:104-110 and the QR of tensor.py:1816 (via the Gram sweep). */
+size_t tnb_gram_workspace_bytes(int dtype, int64_t rows, int64_t n);
+int tnb_gram(int dtype, const void* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
+             void* stream);
+/* Same Gram on the tcgen05 tensor cores: TMA-staged slabs, kind::tf32 MMA, fp32 accumulation in TMEM
+ * (fp32 input only, n % 4 == 0).  Output fp64 G like tnb_gram. */
+size_t tnb_gram_tc_workspace_bytes(int64_t rows, int64_t n);
+int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* C (rows x r) = A (rows x n) * V (n x r), same dtype throughout (fp32: FFMA, fp32 accumulate).
+ * Replaces: `M @ left` round.py:181 / einsum absorb tensor.py:2081-2083. */
+int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream);
+/* Symmetric eigendecomposition of a PSD matrix G (n x n fp64): all eigenpairs by one-CTA parallel
+ * Jacobi (n <= 256), eigenvalues descending in w, eigenvectors in the columns of V (row-major n x n).
+ * Replaces: torch.linalg.eigh round.py:114 / the U,S of torch.linalg.svd round.py:96. */
+size_t tnb_eigh_workspace_bytes(int32_t n);
+int tnb_eigh_jacobi(const double* G, int32_t n, double* w, double* V, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* k leading eigenpairs of PSD G (n x n fp64) by Chebyshev-filtered subspace iteration with block b
+ * (b = 0 -> default 2k): w (b, descending Ritz values), V (n x b row-major, fp64). info_host[0] = #products. */
+size_t tnb_eig_topk_workspace_bytes(int32_t n, int32_t k, int32_t b);
+int tnb_eig_topk(const double* G, int32_t n, int32_t k, int32_t b, double tol, double* w, double* V, void* workspace,
+                 size_t workspace_bytes, double* info_host, void* stream);
+/* Relative reconstruction error ||T - TT(cores)||_F / ||T||_F, accumulated in fp64 on the device
+ * (reference: metrics.relative_error metrics.py:135-151 on Tensor.torch() tensor.py:1639-1687). */
+size_t tnb_tt_relative_error_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* ranks);
+int tnb_tt_relative_error(int dtype, const void* data, const void* const* cores, int ndim, const int64_t* shape,
+                          const int32_t* ranks, void* workspace, size_t workspace_bytes, double* result_host,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNB200_H */

@@ -1,0 +1,41 @@
+"""-m gpu: the tcgen05/TMA Gram kernel against an fp64 reference (TF32 inputs, fp32 accumulate)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(8192, 128), (10000, 64), (4096, 256), (5000, 320), (3001, 100), (2048, 2048), (70000, 32),
+                                   (16384, 512)])
+def test_gram_tc_matches_fp64(shape):
+    from tntorch_b200 import ops
+
+    if not ops.has_tensorcore_path():
+        pytest.fail("tensor-core path unavailable on this device (needs sm_100)")
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(*shape, generator=g, dtype=torch.float32).cuda()
+    G = ops.gram(A, tensorcore=True)
+    torch.cuda.synchronize()
+    ref = A.double().T @ A.double()
+    # TF32 truncation of both operands: relative 2^-10 per product, random sign -> ~1e-3/sqrt(K) of the diagonal scale
+    scale = ref.diagonal().max().item()
+    err = (G - ref).abs().max().item() / scale
+    assert err < 2e-3, err
+    assert torch.equal(G, G.T)
+    # the mean truncation bias shrinks the diagonal by < 2^-10
+    d = (G.diagonal() / ref.diagonal())
+    assert d.min().item() > 1 - 2e-3 and d.max().item() <= 1 + 1e-6
+
+
+def test_gram_tc_structured_exact():
+    """Inputs exactly representable in TF32 must give the exact Gram (catches layout/descriptor errors
+    that random data would hide behind the tolerance)."""
+    from tntorch_b200 import ops
+
+    rows, n = 4096 + 37, 384
+    i = torch.arange(rows, dtype=torch.float64)[:, None]
+    j = torch.arange(n, dtype=torch.float64)[None, :]
+    A = (((i * 7 + j * 13) % 17) - 8).float().cuda()  # small integers
+    G = ops.gram(A, tensorcore=True)
+    ref = A.double().T @ A.double()
+    assert torch.equal(G, ref)

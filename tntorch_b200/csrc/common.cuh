@@ -1,0 +1,138 @@
+// tnb200 — shared helpers for the CUDA translation unit (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tnb200.h"
+
+namespace tnb {
+
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+inline std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+#define TNB_COUNT_LAUNCH() (::tnb::launch_counter().fetch_add(1, std::memory_order_relaxed))
+
+#define TNB_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return ::tnb::fail(TNB_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define TNB_LAUNCH_CHECK()                                                                          \
+  do {                                                                                              \
+    TNB_COUNT_LAUNCH();                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                           \
+    if (e__ != cudaSuccess)                                                                         \
+      return ::tnb::fail(TNB_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define TNB_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != TNB_OK) return rc__; \
+  } while (0)
+
+template <typename T>
+inline T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off = 0;
+  bool ok = true;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (off + bytes > cap) {
+      ok = false;
+      off += bytes;
+      return nullptr;
+    }
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+// Sizing twin of Arena: same calls, only counts.
+struct ArenaSizer {
+  size_t off = 0;
+  bool ok = true;
+  template <typename T>
+  T* take(size_t count) {
+    off += align_up(count * sizeof(T));
+    return nullptr;
+  }
+};
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool valid = false;
+};
+inline const DeviceInfo& device_info() {
+  static thread_local DeviceInfo info;
+  static thread_local int cached_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    info.valid = false;
+    return info;
+  }
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+      info.sm_count = p.multiProcessorCount;
+      info.cc_major = p.major;
+      info.cc_minor = p.minor;
+      info.valid = true;
+      cached_dev = dev;
+    } else {
+      info.valid = false;
+    }
+  }
+  return info;
+}
+
+// Pinned host scratch for reading small results back (ranks, Ritz values).
+inline void* pinned_scratch(size_t bytes) {
+  static thread_local void* p = nullptr;
+  static thread_local size_t cap = 0;
+  if (bytes > cap) {
+    if (p) cudaFreeHost(p);
+    size_t n = bytes < 65536 ? 65536 : bytes;
+    if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess) {
+      p = nullptr;
+      cap = 0;
+      return nullptr;
+    }
+    cap = n;
+  }
+  return p;
+}
+
+}  // namespace tnb

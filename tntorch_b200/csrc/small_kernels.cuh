@@ -1,0 +1,171 @@
+// Glue kernels around the GEMM / eigen kernels: rank rule, factor extraction, traces, fills.
+#pragma once
+#include "common.cuh"
+#include "jacobi.cuh"
+
+namespace tnb {
+
+// Device-side scalars shared by the steps of one sweep.
+struct SweepScalars {
+  double norm2;      // ||T||_F^2  (trace of the first Gram)
+  double delta2;     // absolute tail-energy budget delta^2 (round.py:151)
+  double trace;      // trace of the current Gram
+  double spare[5];
+  int rank;          // chosen rank of the current step
+  int zero_flag;     // 1 when the current unfolding is numerically zero (round.py:137-145)
+  int jacobi_info;   // sweeps used by the last Jacobi solve (negative: not converged)
+  int spare_i[5];
+};
+
+__global__ void trace_kernel(const double* __restrict__ G, int n, int ld, SweepScalars* sc, int set_norm,
+                             double eps_scaled /* (eps/max(1,sqrt(N-1)))^2, used when set_norm */) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += G[(size_t)i * ld + i];
+  s = block_reduce_sum(s, red);
+  if (threadIdx.x == 0) {
+    sc->trace = s;
+    if (set_norm) {
+      sc->norm2 = s;
+      sc->delta2 = eps_scaled * s;
+    }
+  }
+}
+
+__global__ void set_delta2_kernel(SweepScalars* sc, double delta_abs, double eps_rel) {
+  // truncated_svd semantics (round.py:79-82): delta given, or eps * ||M||, or 0
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (delta_abs >= 0.0) sc->delta2 = delta_abs * delta_abs;
+    else if (eps_rel >= 0.0) sc->delta2 = eps_rel * eps_rel * sc->trace;
+    else sc->delta2 = 0.0;
+  }
+}
+
+// round.py:137-158 on descending eigenvalues w (= squared singular values).
+//   full spectrum (topk == 0): w holds all L values.
+//   leading values only (topk == 1): w holds kk >= min(rmax, L) leading Ritz values; the tail energy
+//   behind index k is trace - sum_{i<=k} w_i.
+__global__ void rank_rule_kernel(const double* __restrict__ w, int L, int kk, int rmax, int topk, int batch_mode,
+                                 SweepScalars* sc) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double w0 = w[0] > 0.0 ? w[0] : 0.0;
+  sc->zero_flag = (sqrt(w0) < 1e-13) ? 1 : 0;
+  int cap = L;
+  if (rmax > 0 && rmax < cap) cap = rmax;
+  int rank;
+  if (batch_mode) {
+    rank = cap;
+  } else if (!topk) {
+    double cum = 0.0;
+    int count_true = 0;
+    for (int i = L - 1; i >= 0; --i) {
+      const double v = w[i] > 0.0 ? w[i] : 0.0;
+      cum += v;
+      if (cum <= sc->delta2) ++count_true; else break;
+    }
+    rank = L - count_true;
+    if (rank > cap) rank = cap;
+  } else {
+    // rank = min(cap, L - count_true); only ranks <= cap matter, and tail_k for k < cap is computable
+    double head = 0.0;
+    rank = cap;
+    for (int k = 0; k < cap && k < kk; ++k) {
+      head += (w[k] > 0.0 ? w[k] : 0.0);
+      const double tail = sc->trace - head;  // energy discarded if the rank were k+1
+      if (tail <= sc->delta2) {
+        rank = k + 1;
+        break;
+      }
+    }
+  }
+  if (rank < 1) rank = 1;
+  sc->rank = rank;
+}
+
+// out[i][j] (or out[j][i] when transpose) = V[i][j] * f(w_j) for j < rank, i < rows.
+//   mode 0: f = 1        mode 1: f = 1/sqrt(w_j)        mode 2: f = sqrt(w_j)
+template <typename TOut>
+__global__ void scale_extract_kernel(const double* __restrict__ V, int ldv, int rows, int rank,
+                                     const double* __restrict__ w, TOut* __restrict__ out, int mode, int transpose) {
+  const int64_t total = (int64_t)rows * rank;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int i, j;
+    if (transpose) {  // idx enumerates out[j][i]
+      j = (int)(idx / rows);
+      i = (int)(idx % rows);
+    } else {
+      i = (int)(idx / rank);
+      j = (int)(idx % rank);
+    }
+    double f = 1.0;
+    if (mode != 0) {
+      const double wj = w[j] > 0.0 ? w[j] : 0.0;
+      const double s = sqrt(wj);
+      f = (mode == 1) ? (s > 0.0 ? 1.0 / s : 0.0) : s;
+    }
+    out[idx] = (TOut)(V[(size_t)i * ldv + j] * f);
+  }
+}
+
+template <typename T>
+__global__ void fill_kernel(T* p, int64_t n, T v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+template <typename TIn, typename TOut>
+__global__ void convert_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (TOut)in[i];
+}
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// deterministic pseudo-random block in (-1, 1)
+template <typename T>
+__global__ void random_fill_kernel(T* p, int64_t n, uint32_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = hash_u32((uint32_t)i * 2654435761U + seed) ^ hash_u32((uint32_t)(i >> 32) + 0x9e3779b9U * seed);
+    p[i] = (T)(((double)(h >> 8) + 0.5) * (2.0 / 16777216.0) - 1.0);
+  }
+}
+
+// SVQB step 1: d_i = 1/sqrt(S_ii), S_ij <- d_i S_ij d_j   (one CTA, b <= 256)
+__global__ void svqb_prep_kernel(double* __restrict__ S, int b, double* __restrict__ d) {
+  __shared__ double sd[JACOBI_MAX_N];
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    const double v = S[(size_t)i * b + i];
+    const double di = v > 1e-300 ? 1.0 / sqrt(v) : 0.0;
+    sd[i] = di;
+    d[i] = di;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+    const int i = idx / b, j = idx % b;
+    S[idx] *= sd[i] * sd[j];
+  }
+}
+// SVQB step 2: T_ij = d_i Q_ij / sqrt(max(lam_j, lam_0 * floor))
+template <typename TB>
+__global__ void svqb_finish_kernel(const double* __restrict__ Q, const double* __restrict__ lam,
+                                   const double* __restrict__ d, int b, double floor_rel, TB* __restrict__ T) {
+  const double lmax = lam[0] > 0.0 ? lam[0] : 0.0;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < b * b; idx += gridDim.x * blockDim.x) {
+    const int i = idx / b, j = idx % b;
+    double lj = lam[j];
+    const double fl = lmax * floor_rel;
+    if (lj < fl) lj = fl;
+    T[idx] = (TB)(lj > 0.0 ? d[i] * Q[idx] / sqrt(lj) : 0.0);
+  }
+}
+
+inline int grid_for(int64_t n, int block = 256, int cap = 4096) {
+  int64_t g = ceil_div<int64_t>(n, block);
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace tnb

@@ -1,0 +1,315 @@
+// Host orchestration of the right-to-left Gram sweep (dense TT-SVD), the TT rounding sweeps and
+// the two-factor split.  Each routine is written once over an arena type so that the very same
+// sequence of `take` calls sizes the workspace (ArenaSizer) and carves it (Arena).
+//
+// Dense TT-SVD (tn.Tensor(data, ranks_tt=r): tensor.py:401-408 -> round_tt tensor.py:2008-2083):
+//   C <- T viewed (rows x I_{N-1});  for mu = N-1 .. 1:
+//     G = C^T C (or C C^T when rows < cols)      Gram, fp64 accumulation   [replaces QR tensor.py:1816 + SVD round.py:96]
+//     (lambda, V) = leading eigenpairs of G       Jacobi / Chebyshev subspace iteration
+//     rank by the tail-energy rule                round.py:147-158
+//     core_mu = V_r^T, C <- C V_r                 round.py:166-172 + tensor.py:2078-2083
+//   core_0 = C.
+// This is algebraically the reference's result (same subspaces, same gauge: cores 1..N-1 have
+// orthonormal right unfoldings, core 0 carries the norm) without the identity-flanked full-rank TT.
+#pragma once
+#include "common.cuh"
+#include "eig.cuh"
+#include "gemm_generic.cuh"
+#include "jacobi.cuh"
+#include "small_kernels.cuh"
+#include "gram_tc.cuh"
+
+namespace tnb {
+
+constexpr int64_t TC_MIN_ROWS = 8192;  // below this the generic fp64-accumulating Gram is used
+
+struct SweepDims {
+  int N = 0;
+  std::vector<int64_t> shape;
+  std::vector<int64_t> rows;   // rows[mu] = prod_{j<mu} shape[j]
+  std::vector<int64_t> rcap;   // rcap[k], k=0..N : max possible rank at bond k
+  std::vector<int64_t> slot;   // element offset of core k in the cores buffer
+  int64_t capacity = 0;
+};
+
+inline int make_dims(int ndim, const int64_t* shape, const int32_t* rmax, SweepDims& d) {
+  if (ndim < 1 || ndim > 62) return fail(TNB_ERR_INVALID, "ndim=%d out of range", ndim);
+  d.N = ndim;
+  d.shape.assign(shape, shape + ndim);
+  for (int k = 0; k < ndim; ++k)
+    if (shape[k] < 1) return fail(TNB_ERR_INVALID, "shape[%d]=%lld must be >= 1", k, (long long)shape[k]);
+  d.rows.assign(ndim + 1, 1);
+  for (int k = 0; k < ndim; ++k) {
+    if (d.rows[k] > (int64_t)1 << 56) return fail(TNB_ERR_INVALID, "tensor too large");
+    d.rows[k + 1] = d.rows[k] * shape[k];
+  }
+  d.rcap.assign(ndim + 1, 1);
+  for (int mu = ndim - 1; mu >= 1; --mu) {
+    int64_t c = shape[mu] * d.rcap[mu + 1];
+    if (d.rows[mu] < c) c = d.rows[mu];
+    if (rmax && rmax[mu - 1] > 0 && rmax[mu - 1] < c) c = rmax[mu - 1];
+    d.rcap[mu] = c;
+  }
+  d.slot.assign(ndim, 0);
+  int64_t off = 0;
+  for (int k = 0; k < ndim; ++k) {
+    d.slot[k] = off;
+    off += d.rcap[k] * shape[k] * d.rcap[k + 1];
+    off = (off + 63) / 64 * 64;  // keep every core 256-byte aligned for fp32
+  }
+  d.capacity = off;
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram of a (rows x n) row-major matrix on whichever side is smaller, into fp64 G (L x L).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct GramWork {
+  double* partial = nullptr;
+  size_t partial_elems = 0;
+  void* tc_ws = nullptr;
+  size_t tc_bytes = 0;
+};
+
+template <typename T, class ArenaT>
+inline void gram_carve(ArenaT& ar, int64_t rows, int64_t n, bool allow_tc, GramWork<T>& w) {
+  const bool tall = rows >= n;
+  const int64_t L = tall ? n : rows;
+  const int64_t K = tall ? rows : n;
+  GemmPlan pl = plan_gemm(L, L, K, true);
+  w.partial_elems = pl.partial_elems;
+  w.partial = ar.template take<double>(pl.partial_elems);
+  w.tc_bytes = 0;
+  w.tc_ws = nullptr;
+  if (allow_tc && std::is_same<T, float>::value && tall && rows >= TC_MIN_ROWS && gram_tc_shape_ok(rows, n)) {
+    w.tc_bytes = gram_tc_workspace_bytes(rows, n);
+    w.tc_ws = ar.template take<char>(w.tc_bytes);
+  }
+}
+
+template <typename T>
+inline int gram_small_side(const T* C, int64_t rows, int64_t n, double* G, float* Gf, GramWork<T>& w, bool use_tc,
+                           int* used_tc, cudaStream_t st) {
+  const bool tall = rows >= n;
+  if (used_tc) *used_tc = 0;
+  if (tall) {
+    if (use_tc && w.tc_ws && std::is_same<T, float>::value) {
+      if (used_tc) *used_tc = 1;
+      return gram_tc_f32(reinterpret_cast<const float*>(C), rows, n, G, Gf, w.tc_ws, w.tc_bytes, st);
+    }
+    GemmPlan pl = plan_gemm(n, n, rows, true);
+    return gemm_splitk<T, T, double, double, float>(pl, n, n, rows, C, n, false, C, n, false, w.partial, G, n, 1.0,
+                                                    nullptr, 0, 0.0, nullptr, 0, 0.0, true, Gf, n, st);
+  }
+  GemmPlan pl = plan_gemm(rows, rows, n, true);
+  return gemm_splitk<T, T, double, double, float>(pl, rows, rows, n, C, n, true, C, n, true, w.partial, G, rows, 1.0,
+                                                  nullptr, 0, 0.0, nullptr, 0, 0.0, true, Gf, rows, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eigen stage: all eigenpairs (Jacobi) when L <= JACOBI_MAX_N, else k leading pairs (ChFSI).
+// Outputs: w (>= L or b doubles, descending), V (L x ldv doubles, columns = vectors).
+// ---------------------------------------------------------------------------------------------
+template <typename TBk>
+struct EigWork {
+  double* w = nullptr;
+  double* V = nullptr;
+  int ldv = 0;
+  double* jscratch = nullptr;
+  int* jinfo = nullptr;
+  bool chfsi = false;
+  int k = 0, b = 0;
+  TBk* Gb = nullptr;  // G in block precision (ChFSI only)
+  ChfsiWork<TBk> cw;
+};
+
+template <typename TBk, class ArenaT>
+inline int eig_carve(ArenaT& ar, int64_t L, int64_t rcap, bool have_rmax, EigWork<TBk>& e) {
+  if (L <= JACOBI_MAX_N) {
+    e.chfsi = false;
+    e.w = ar.template take<double>(L);
+    e.V = ar.template take<double>((size_t)L * L);
+    e.ldv = (int)L;
+    e.jscratch = ar.template take<double>(jacobi_scratch_doubles((int)L));
+    e.jinfo = ar.template take<int>(4);
+    return TNB_OK;
+  }
+  if (!have_rmax)
+    return fail(TNB_ERR_UNSUPPORTED,
+                "eps-only truncation needs the full spectrum of a %lld x %lld Gram matrix; pass rmax / ranks_tt "
+                "(direct eigensolver limit is %d)", (long long)L, (long long)L, JACOBI_MAX_N);
+  if (rcap + 16 > JACOBI_MAX_N)
+    return fail(TNB_ERR_UNSUPPORTED, "target rank %lld too large for the subspace eigensolver (limit %d) at Gram size %lld",
+                (long long)rcap, JACOBI_MAX_N - 16, (long long)L);
+  if (L > 46000) return fail(TNB_ERR_UNSUPPORTED, "Gram size %lld too large", (long long)L);
+  e.chfsi = true;
+  e.k = (int)rcap;
+  e.b = chfsi_default_block((int)L, e.k);
+  e.w = ar.template take<double>(e.b);
+  e.V = ar.template take<double>((size_t)L * e.b);
+  e.ldv = e.b;
+  if (!std::is_same<TBk, double>::value) e.Gb = ar.template take<TBk>((size_t)L * L);
+  chfsi_carve<TBk>(ar, (int)L, e.b, e.cw);
+  return TNB_OK;
+}
+
+template <typename TBk>
+inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e, const double* d_trace,
+                   ChfsiStats* stats, cudaStream_t st) {
+  if (!e.chfsi) return jacobi_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
+  const TBk* Gb = Gb_in;
+  if (std::is_same<TBk, double>::value) Gb = reinterpret_cast<const TBk*>(G);
+  return eig_topk_chfsi<TBk>(Gb, (int)L, e.k, e.b, d_trace, 1e-6, e.cw, e.w, e.V, stats, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One truncation step, shared by the dense sweep and by phase B of TT rounding.
+//   C (rows x n, row-major)  ->  core (rank x n, orthonormal rows)  and  Cn (rows x rank) with
+//   C ~= Cn * core, exactly what tn.truncated_svd(M, left_ortho=False) returns (round.py:166-172,181)
+//   for M = the right unfolding the reference holds at tensor.py:2054.
+// ---------------------------------------------------------------------------------------------
+struct SweepInfo {
+  double norm = 0;
+  int eig_solves = 0;
+  int chfsi_products = 0;
+  int tc_grams = 0;
+};
+
+struct StepCtx {
+  SweepScalars* sc = nullptr;   // device
+  int* h_sc = nullptr;          // pinned host mirror
+  uint32_t flags = 0;
+  bool allow_tc = false;
+  double eps_scaled2 = 0;       // (eps / max(1, sqrt(N-1)))^2
+  SweepInfo* info = nullptr;
+  cudaStream_t st = 0;
+};
+
+template <typename T, class ArenaT>
+inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, int64_t rows, int64_t n, int64_t rank_cap,
+                         bool have_rmax, int32_t rm, bool first_step, T* core, T* Cn, int64_t* rank_out) {
+  typedef T TBk;  // block precision of the subspace eigensolver follows the data
+  const bool tall = rows >= n;
+  const int64_t L = tall ? n : rows;
+  const int batch_mode = (cx.flags & TNB_FLAG_BATCH_MODE) ? 1 : 0;
+  cudaStream_t st = cx.st;
+  GramWork<T> gw;
+  EigWork<TBk> ew;
+  gram_carve<T>(ar, rows, n, cx.allow_tc, gw);
+  double* G = ar.template take<double>((size_t)L * L);
+  float* Gf = nullptr;
+  const int64_t kcap = std::min<int64_t>(rank_cap, L);
+  TNB_TRY(eig_carve<TBk>(ar, L, kcap, have_rmax, ew));
+  if (ew.chfsi && std::is_same<TBk, float>::value) Gf = reinterpret_cast<float*>(ew.Gb);
+  T* fac = ar.template take<T>((size_t)L * (size_t)kcap);  // V_r or U_r/s
+  if (dry) return TNB_OK;
+  if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "workspace too small (need > %zu bytes)", ar.off);
+  int used_tc = 0;
+  TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, cx.allow_tc, &used_tc, st));
+  if (cx.info) cx.info->tc_grams += used_tc;
+  trace_kernel<<<1, 256, 0, st>>>(G, (int)L, (int)L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
+  TNB_LAUNCH_CHECK();
+  ChfsiStats cs;
+  TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st));
+  if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products;
+  rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, cx.sc);
+  TNB_LAUNCH_CHECK();
+  TNB_CUDA(cudaMemcpyAsync(cx.h_sc, cx.sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(cudaStreamSynchronize(st));
+  const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(cx.h_sc);
+  if (first_step && cx.info) cx.info->norm = std::sqrt(hs->norm2 > 0 ? hs->norm2 : 0.0);
+  int64_t rank = hs->rank;
+  if (rank > kcap) rank = kcap;
+  if (hs->zero_flag) {  // round.py:137-145: rank-1 zero factors
+    rank = 1;
+    fill_kernel<T><<<grid_for(n), 256, 0, st>>>(core, n, (T)0);
+    TNB_LAUNCH_CHECK();
+    fill_kernel<T><<<grid_for(rows), 256, 0, st>>>(Cn, rows, (T)0);
+    TNB_LAUNCH_CHECK();
+  } else if (tall) {
+    // core = V_r^T (rank x n);  Cn = C V_r
+    scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)n, (int)rank, ew.w, core, 0, 1);
+    TNB_LAUNCH_CHECK();
+    scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)n, (int)rank, ew.w, fac, 0, 0);
+    TNB_LAUNCH_CHECK();
+    TNB_TRY((gemm_direct<T, T, T, T>(rows, rank, n, C, n, true, fac, rank, false, Cn, rank, (T)1, nullptr, 0, (T)0,
+                                     nullptr, 0, (T)0, st)));
+  } else {
+    // core = diag(1/s) U_r^T C (rank x n);  Cn = U_r diag(s)
+    scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, fac, 1, 0);
+    TNB_LAUNCH_CHECK();
+    TNB_TRY((gemm_direct<T, T, T, T>(rank, n, rows, fac, rank, false, C, n, false, core, n, (T)1, nullptr, 0, (T)0,
+                                     nullptr, 0, (T)0, st)));
+    scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, Cn, 2, 0);
+    TNB_LAUNCH_CHECK();
+  }
+  *rank_out = rank;
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense TT-SVD
+// ---------------------------------------------------------------------------------------------
+template <typename T, class ArenaT>
+inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, const int32_t* rmax, double eps,
+                      uint32_t flags, T* cores, int32_t* ranks_host, SweepInfo* info, cudaStream_t st) {
+  const int N = d.N;
+  StepCtx cx;
+  cx.flags = flags;
+  cx.allow_tc = !(flags & TNB_FLAG_NO_TENSORCORE) && (dry || tc_path_available());
+  cx.info = info;
+  cx.st = st;
+  const double epsN = eps / std::max(1.0, std::sqrt((double)(N - 1)));
+  cx.eps_scaled2 = epsN * epsN;
+  cx.sc = ar.template take<SweepScalars>(1);
+  if (!dry) {
+    cx.h_sc = static_cast<int*>(pinned_scratch(sizeof(SweepScalars)));
+    if (!cx.h_sc) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
+    ranks_host[0] = 1;
+    ranks_host[N] = 1;
+  }
+  if (N == 1) {
+    if (!dry) {
+      TNB_CUDA(cudaMemcpyAsync(cores + d.slot[0], data, sizeof(T) * d.shape[0], cudaMemcpyDeviceToDevice, st));
+      TNB_CUDA(cudaStreamSynchronize(st));
+      if (info) info->norm = 0;
+    }
+    return TNB_OK;
+  }
+  // carry buffers (ping-pong), sized by the rank caps
+  size_t carry_elems[2] = {0, 0};
+  for (int mu = N - 1, t = 0; mu >= 1; --mu, ++t) {
+    const size_t e = (size_t)d.rows[mu] * (size_t)d.rcap[mu];
+    if (e > carry_elems[t & 1]) carry_elems[t & 1] = e;
+  }
+  T* carry[2] = {ar.template take<T>(carry_elems[0]), ar.template take<T>(carry_elems[1])};
+  const T* C = data;
+  int64_t r_next = 1;
+  size_t peak = ar.off;
+  for (int mu = N - 1, t = 0; mu >= 1; --mu, ++t) {
+    const int64_t rows = d.rows[mu];
+    const int64_t n = dry ? d.shape[mu] * d.rcap[mu + 1] : d.shape[mu] * r_next;
+    const bool have_rmax = rmax && rmax[mu - 1] > 0;
+    const size_t mark = ar.off;
+    int64_t rank = d.rcap[mu];
+    TNB_TRY((truncate_step<T>(ar, dry, cx, C, rows, n, d.rcap[mu], have_rmax, have_rmax ? rmax[mu - 1] : 0, t == 0,
+                              dry ? nullptr : cores + d.slot[mu], carry[t & 1], &rank)));
+    if (!dry) {
+      ranks_host[mu] = (int32_t)rank;
+      r_next = rank;
+      C = carry[t & 1];
+    }
+    if (ar.off > peak) peak = ar.off;  // the sizing pass reports the largest step
+    ar.off = mark;                     // release the step scratch
+  }
+  if (dry) ar.off = peak;
+  if (!dry) {
+    TNB_CUDA(cudaMemcpyAsync(cores + d.slot[0], C, sizeof(T) * (size_t)d.shape[0] * (size_t)r_next,
+                             cudaMemcpyDeviceToDevice, st));
+    TNB_CUDA(cudaStreamSynchronize(st));
+  }
+  return TNB_OK;
+}
+
+}  // namespace tnb

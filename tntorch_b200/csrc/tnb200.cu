@@ -1,0 +1,329 @@
+// tnb200 — single translation unit: C-ABI entry points declared in include/tnb200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
+#include "common.cuh"
+#include "gemm_generic.cuh"
+#include "jacobi.cuh"
+#include "small_kernels.cuh"
+#include "eig.cuh"
+#include "gram_tc.cuh"
+#include "sweep.cuh"
+#include "round_impl.cuh"
+
+using namespace tnb;
+
+namespace {
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int check_dtype(int dtype) {
+  if (dtype != TNB_F32 && dtype != TNB_F64) return fail(TNB_ERR_INVALID, "dtype must be TNB_F32 or TNB_F64, got %d", dtype);
+  return TNB_OK;
+}
+inline int require_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || !device_info().valid) {
+    cudaGetLastError();
+    return fail(TNB_ERR_CUDA, "no CUDA device available: tnb200 has no CPU fallback");
+  }
+  return TNB_OK;
+}
+// headroom for rank-dependent re-planning between the sizing pass (rank caps) and the run (actual ranks)
+inline size_t with_slack(size_t bytes) { return bytes + bytes / 8 + (size_t)(4 << 20); }
+}  // namespace
+
+extern "C" {
+
+int tnb_version(void) { return 100; }
+const char* tnb_last_error(void) { return last_error_ref().c_str(); }
+uint64_t tnb_launch_count(void) { return launch_counter().load(); }
+int tnb_has_tensorcore_path(void) { return tc_path_available() ? 1 : 0; }
+
+// ------------------------------------------------------------------ dense TT-SVD
+int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host) {
+  SweepDims d;
+  if (make_dims(ndim, shape, rmax, d) != TNB_OK) return -1;
+  if (core_offsets_host)
+    for (int k = 0; k < ndim; ++k) core_offsets_host[k] = d.slot[k];
+  return d.capacity;
+}
+
+size_t tnb_ttsvd_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* rmax, uint32_t flags) {
+  SweepDims d;
+  if (check_dtype(dtype) != TNB_OK || make_dims(ndim, shape, rmax, d) != TNB_OK) return 0;
+  ArenaSizer ar;
+  int rc;
+  if (dtype == TNB_F32)
+    rc = ttsvd_impl<float>(ar, true, nullptr, d, rmax, 0.0, flags, nullptr, nullptr, nullptr, 0);
+  else
+    rc = ttsvd_impl<double>(ar, true, nullptr, d, rmax, 0.0, flags, nullptr, nullptr, nullptr, 0);
+  if (rc != TNB_OK) return 0;
+  return with_slack(ar.off);
+}
+
+int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
+              uint32_t flags, void* workspace, size_t workspace_bytes, void* cores, int64_t cores_capacity,
+              int32_t* ranks_host, double* info_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!data || !shape || !cores || !ranks_host || !workspace) return fail(TNB_ERR_INVALID, "tnb_ttsvd: null argument");
+  if (rmax)
+    for (int k = 0; k < ndim - 1; ++k)
+      if (rmax[k] < 0) return fail(TNB_ERR_INVALID, "rmax[%d] must be >= 1 (or 0 for none)", k);
+  SweepDims d;
+  TNB_TRY(make_dims(ndim, shape, rmax, d));
+  if (cores_capacity < d.capacity)
+    return fail(TNB_ERR_WORKSPACE, "tnb_ttsvd: cores buffer holds %lld elements, need %lld", (long long)cores_capacity,
+                (long long)d.capacity);
+  Arena ar(workspace, workspace_bytes);
+  SweepInfo info;
+  int rc;
+  if (dtype == TNB_F32)
+    rc = ttsvd_impl<float>(ar, false, static_cast<const float*>(data), d, rmax, eps, flags, static_cast<float*>(cores),
+                           ranks_host, &info, as_stream(stream));
+  else
+    rc = ttsvd_impl<double>(ar, false, static_cast<const double*>(data), d, rmax, eps, flags,
+                            static_cast<double*>(cores), ranks_host, &info, as_stream(stream));
+  if (info_host) {
+    for (int i = 0; i < 8; ++i) info_host[i] = 0.0;
+    info_host[0] = info.norm;
+    info_host[1] = info.eig_solves;
+    info_host[2] = info.chfsi_products;
+    info_host[3] = info.tc_grams;
+  }
+  return rc;
+}
+
+int tnb_ttsvd_host(int dtype, const void* data_host, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
+                   uint32_t flags, void* device_buffer, void* workspace, size_t workspace_bytes, void* cores_dev,
+                   int64_t cores_capacity, void* cores_host, int32_t* ranks_host, double* info_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!data_host || !device_buffer || !cores_host) return fail(TNB_ERR_INVALID, "tnb_ttsvd_host: null argument");
+  SweepDims d;
+  TNB_TRY(make_dims(ndim, shape, rmax, d));
+  const size_t esz = dtype == TNB_F32 ? 4 : 8;
+  const size_t total = (size_t)d.rows[ndim] * esz;
+  cudaStream_t st = as_stream(stream);
+  // chunked so that a pageable source still overlaps its staging copies with the DMA
+  const size_t chunk = (size_t)256 << 20;
+  for (size_t off = 0; off < total; off += chunk) {
+    const size_t nb = total - off < chunk ? total - off : chunk;
+    TNB_CUDA(cudaMemcpyAsync(static_cast<char*>(device_buffer) + off, static_cast<const char*>(data_host) + off, nb,
+                             cudaMemcpyHostToDevice, st));
+  }
+  TNB_TRY(tnb_ttsvd(dtype, device_buffer, ndim, shape, rmax, eps, flags, workspace, workspace_bytes, cores_dev,
+                    cores_capacity, ranks_host, info_host, stream));
+  TNB_CUDA(cudaMemcpyAsync(cores_host, cores_dev, (size_t)d.capacity * esz, cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(cudaStreamSynchronize(st));
+  return TNB_OK;
+}
+
+// ------------------------------------------------------------------ TT rounding
+int64_t tnb_tt_round_cores_capacity(int ndim, const int64_t* shape, const int32_t* ranks_in, const int32_t* rmax,
+                                    int64_t* core_offsets_host) {
+  RoundDims d;
+  if (make_round_dims(ndim, shape, ranks_in, rmax, d) != TNB_OK) return -1;
+  if (core_offsets_host)
+    for (int k = 0; k < ndim; ++k) core_offsets_host[k] = d.slot[k];
+  return d.capacity;
+}
+
+size_t tnb_tt_round_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                    const int32_t* rmax) {
+  RoundDims d;
+  if (check_dtype(dtype) != TNB_OK || make_round_dims(ndim, shape, ranks_in, rmax, d) != TNB_OK) return 0;
+  ArenaSizer ar;
+  int rc;
+  if (dtype == TNB_F32)
+    rc = tt_round_impl<float>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
+  else
+    rc = tt_round_impl<double>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
+  if (rc != TNB_OK) return 0;
+  return with_slack(ar.off);
+}
+
+int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                 const int32_t* rmax, double eps, uint32_t flags, void* workspace, size_t workspace_bytes,
+                 void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!cores_in || !shape || !ranks_in || !cores_out || !ranks_host || !workspace)
+    return fail(TNB_ERR_INVALID, "tnb_tt_round: null argument");
+  RoundDims d;
+  TNB_TRY(make_round_dims(ndim, shape, ranks_in, rmax, d));
+  if (cores_capacity < d.capacity)
+    return fail(TNB_ERR_WORKSPACE, "tnb_tt_round: cores buffer holds %lld elements, need %lld",
+                (long long)cores_capacity, (long long)d.capacity);
+  Arena ar(workspace, workspace_bytes);
+  if (dtype == TNB_F32)
+    return tt_round_impl<float>(ar, false, reinterpret_cast<const float* const*>(cores_in), d, rmax, eps, flags,
+                                static_cast<float*>(cores_out), ranks_host, as_stream(stream));
+  return tt_round_impl<double>(ar, false, reinterpret_cast<const double* const*>(cores_in), d, rmax, eps, flags,
+                               static_cast<double*>(cores_out), ranks_host, as_stream(stream));
+}
+
+// ------------------------------------------------------------------ truncated_svd
+size_t tnb_truncated_svd_workspace_bytes(int dtype, int64_t m, int64_t n) {
+  if (check_dtype(dtype) != TNB_OK || m < 1 || n < 1) return 0;
+  ArenaSizer ar;
+  int rc;
+  // sized for the worst admissible request (rmax up to the subspace-solver limit)
+  const int32_t rmax_cap = JACOBI_MAX_N - 16;
+  if (dtype == TNB_F32)
+    rc = truncated_svd_impl<float>(ar, true, nullptr, m, n, -1, -1, rmax_cap, 1, nullptr, nullptr, nullptr, 0);
+  else
+    rc = truncated_svd_impl<double>(ar, true, nullptr, m, n, -1, -1, rmax_cap, 1, nullptr, nullptr, nullptr, 0);
+  if (rc != TNB_OK) return 0;
+  return with_slack(ar.off);
+}
+
+int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double delta, double eps, int32_t rmax,
+                      int left_ortho, void* workspace, size_t workspace_bytes, void* left, void* right,
+                      int32_t* rank_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!M || !left || !right || !rank_host || !workspace) return fail(TNB_ERR_INVALID, "tnb_truncated_svd: null argument");
+  if (m < 1 || n < 1) return fail(TNB_ERR_INVALID, "tnb_truncated_svd: empty matrix");
+  if (delta >= 0 && eps >= 0) return fail(TNB_ERR_INVALID, "Provide either `delta` or `eps`");  // round.py:77-78
+  if (rmax < 0) return fail(TNB_ERR_INVALID, "rmax must be >= 1");                               // round.py:85
+  Arena ar(workspace, workspace_bytes);
+  if (dtype == TNB_F32)
+    return truncated_svd_impl<float>(ar, false, static_cast<const float*>(M), m, n, delta, eps, rmax, left_ortho,
+                                     static_cast<float*>(left), static_cast<float*>(right), rank_host, as_stream(stream));
+  return truncated_svd_impl<double>(ar, false, static_cast<const double*>(M), m, n, delta, eps, rmax, left_ortho,
+                                    static_cast<double*>(left), static_cast<double*>(right), rank_host,
+                                    as_stream(stream));
+}
+
+// ------------------------------------------------------------------ building blocks
+size_t tnb_gram_workspace_bytes(int dtype, int64_t rows, int64_t n) {
+  if (check_dtype(dtype) != TNB_OK || rows < 1 || n < 1) return 0;
+  GemmPlan pl = plan_gemm(n, n, rows, true);
+  return align_up(pl.partial_elems * sizeof(double)) + 256;
+}
+
+int tnb_gram(int dtype, const void* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
+             void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!A || !G || !workspace || rows < 1 || n < 1) return fail(TNB_ERR_INVALID, "tnb_gram: bad argument");
+  GemmPlan pl = plan_gemm(n, n, rows, true);
+  if (workspace_bytes < pl.partial_elems * sizeof(double)) return fail(TNB_ERR_WORKSPACE, "tnb_gram: workspace too small");
+  double* partial = static_cast<double*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == TNB_F32)
+    return gemm_splitk<float, float, double, double, float>(pl, n, n, rows, static_cast<const float*>(A), n, false,
+                                                            static_cast<const float*>(A), n, false, partial, G, n, 1.0,
+                                                            nullptr, 0, 0.0, nullptr, 0, 0.0, true, (float*)nullptr, 0, st);
+  return gemm_splitk<double, double, double, double, float>(pl, n, n, rows, static_cast<const double*>(A), n, false,
+                                                            static_cast<const double*>(A), n, false, partial, G, n, 1.0,
+                                                            nullptr, 0, 0.0, nullptr, 0, 0.0, true, (float*)nullptr, 0, st);
+}
+
+size_t tnb_gram_tc_workspace_bytes(int64_t rows, int64_t n) {
+  if (!gram_tc_shape_ok(rows, n)) return 0;
+  return gram_tc_workspace_bytes(rows, n) + 256;
+}
+
+int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !G || !workspace) return fail(TNB_ERR_INVALID, "tnb_gram_tc_f32: null argument");
+  return gram_tc_f32(A, rows, n, G, nullptr, workspace, workspace_bytes, as_stream(stream));
+}
+
+int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!A || !V || !C || rows < 1 || n < 1 || r < 1) return fail(TNB_ERR_INVALID, "tnb_project: bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == TNB_F32)
+    return gemm_direct<float, float, float, float>(rows, r, n, static_cast<const float*>(A), n, true,
+                                                   static_cast<const float*>(V), r, false, static_cast<float*>(C), r, 1.f,
+                                                   nullptr, 0, 0.f, nullptr, 0, 0.f, st);
+  return gemm_direct<double, double, double, double>(rows, r, n, static_cast<const double*>(A), n, true,
+                                                     static_cast<const double*>(V), r, false, static_cast<double*>(C), r,
+                                                     1.0, nullptr, 0, 0.0, nullptr, 0, 0.0, st);
+}
+
+size_t tnb_eigh_workspace_bytes(int32_t n) {
+  if (n < 1 || n > JACOBI_MAX_N) return 0;
+  return align_up(jacobi_scratch_doubles(n) * sizeof(double)) + 256;
+}
+
+int tnb_eigh_jacobi(const double* G, int32_t n, double* w, double* V, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  TNB_TRY(require_device());
+  if (!G || !w || !V || !workspace) return fail(TNB_ERR_INVALID, "tnb_eigh_jacobi: null argument");
+  if (n < 1 || n > JACOBI_MAX_N) return fail(TNB_ERR_UNSUPPORTED, "tnb_eigh_jacobi: n=%d outside [1,%d]", n, JACOBI_MAX_N);
+  Arena ar(workspace, workspace_bytes);
+  double* js = ar.take<double>(jacobi_scratch_doubles(n));
+  int* jinfo = ar.take<int>(4);
+  if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tnb_eigh_jacobi: workspace too small");
+  return jacobi_eigh(G, n, n, w, V, js, jinfo, as_stream(stream));
+}
+
+size_t tnb_eig_topk_workspace_bytes(int32_t n, int32_t k, int32_t b) {
+  if (n < 1 || k < 1) return 0;
+  if (b <= 0) b = chfsi_default_block(n, k);
+  ArenaSizer ar;
+  ChfsiWork<double> w;
+  chfsi_carve<double>(ar, n, b, w);
+  return ar.off + 4096;
+}
+
+int tnb_eig_topk(const double* G, int32_t n, int32_t k, int32_t b, double tol, double* w, double* V, void* workspace,
+                 size_t workspace_bytes, double* info_host, void* stream) {
+  TNB_TRY(require_device());
+  if (!G || !w || !V || !workspace) return fail(TNB_ERR_INVALID, "tnb_eig_topk: null argument");
+  if (b <= 0) b = chfsi_default_block(n, k);
+  if (k < 1 || k > b || b > n) return fail(TNB_ERR_INVALID, "tnb_eig_topk: need 1 <= k <= b <= n");
+  Arena ar(workspace, workspace_bytes);
+  ChfsiWork<double> cw;
+  chfsi_carve<double>(ar, n, b, cw);
+  double* d_trace = ar.take<double>(4);
+  if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tnb_eig_topk: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  SweepScalars* sc = reinterpret_cast<SweepScalars*>(ar.take<SweepScalars>(1));
+  if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tnb_eig_topk: workspace too small");
+  trace_kernel<<<1, 256, 0, st>>>(G, n, n, sc, 0, 0.0);
+  TNB_LAUNCH_CHECK();
+  (void)d_trace;
+  ChfsiStats cs;
+  int rc = eig_topk_chfsi<double>(G, n, k, b, &sc->trace, tol > 0 ? tol : 1e-6, cw, w, V, &cs, st);
+  if (info_host) {
+    info_host[0] = cs.products;
+    info_host[1] = cs.outer;
+    info_host[2] = cs.converged;
+  }
+  if (rc == TNB_OK) TNB_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+size_t tnb_tt_relative_error_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* ranks) {
+  if (check_dtype(dtype) != TNB_OK || ndim < 2) return 0;
+  ArenaSizer ar;
+  int rc;
+  if (dtype == TNB_F32)
+    rc = tt_relative_error_impl<float>(ar, true, nullptr, nullptr, ndim, shape, ranks, nullptr, 0);
+  else
+    rc = tt_relative_error_impl<double>(ar, true, nullptr, nullptr, ndim, shape, ranks, nullptr, 0);
+  return rc == TNB_OK ? ar.off + 4096 : 0;
+}
+
+int tnb_tt_relative_error(int dtype, const void* data, const void* const* cores, int ndim, const int64_t* shape,
+                          const int32_t* ranks, void* workspace, size_t workspace_bytes, double* result_host,
+                          void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!data || !cores || !shape || !ranks || !workspace || !result_host)
+    return fail(TNB_ERR_INVALID, "tnb_tt_relative_error: null argument");
+  Arena ar(workspace, workspace_bytes);
+  if (dtype == TNB_F32)
+    return tt_relative_error_impl<float>(ar, false, static_cast<const float*>(data),
+                                         reinterpret_cast<const float* const*>(cores), ndim, shape, ranks, result_host,
+                                         as_stream(stream));
+  return tt_relative_error_impl<double>(ar, false, static_cast<const double*>(data),
+                                        reinterpret_cast<const double* const*>(cores), ndim, shape, ranks, result_host,
+                                        as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""Thin torch-tensor wrappers over the C-ABI (device pointers in, torch tensors out).
+
+PyTorch is plumbing here: device memory (caching allocator), the current stream and
+``torch.distributed``.  All arithmetic happens inside libtnb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, i32, i64, lib
+
+_DT = {torch.float32: _lib.TNB_F32, torch.float64: _lib.TNB_F64}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype not in _DT:
+        raise ValueError(f"tntorch_b200 supports float32/float64 tensors, got {t.dtype}")
+    return _DT[t.dtype]
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor must live on a CUDA device (tntorch_b200 has no CPU path)")
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _rmax_list(rmax, nbonds: int) -> List[int]:
+    """Reference convention (tensor.py:2027-2029): scalar or list of N-1; None = no cap."""
+    if not hasattr(rmax, "__len__"):
+        rmax = [rmax] * nbonds
+    assert len(rmax) == nbonds
+    out = []
+    for r in rmax:
+        if r is None:
+            out.append(0)
+        else:
+            r = int(r)
+            assert r >= 1
+            out.append(min(r, 2**31 - 1))
+    return out
+
+
+def launch_count() -> int:
+    return int(lib().tnb_launch_count())
+
+
+def has_tensorcore_path() -> bool:
+    return bool(lib().tnb_has_tensorcore_path())
+
+
+# --------------------------------------------------------------------------------------
+def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = False, use_tensorcore: bool = True,
+          return_info: bool = False):
+    """Dense tensor -> list of TT cores [r_{k-1}, I_k, r_k] (tn.Tensor(data, ranks_tt=...), tensor.py:401-408)."""
+    _require_cuda(data, "ttsvd")
+    data = data.contiguous()
+    code = _dtype_code(data)
+    N = data.dim()
+    shape = list(data.shape)
+    rm = _rmax_list(rmax, max(N - 1, 0))
+    flags = (0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_BATCH_MODE if batch_mode else 0)
+    L = lib()
+    sh = i64(shape)
+    rmc = i32(rm) if N > 1 else i32([0])
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_ttsvd_cores_capacity(N, sh, rmc, offs)
+    if cap < 0:
+        check(_lib.ERR_INVALID)
+    wsb = L.tnb_ttsvd_workspace_bytes(code, N, sh, rmc, flags)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED if L.tnb_last_error() else _lib.ERR_INVALID)
+    ws = _ws(wsb, data.device)
+    cores_buf = torch.empty(int(cap), dtype=data.dtype, device=data.device)
+    ranks = (C.c_int32 * (N + 1))()
+    info = (C.c_double * 8)()
+    with torch.cuda.device(data.device):
+        check(L.tnb_ttsvd(code, _ptr(data), N, sh, rmc, float(eps), flags, _ptr(ws), ws.numel(), _ptr(cores_buf), cap,
+                          ranks, info, _stream()))
+    cores = []
+    for k in range(N):
+        r0, r1 = ranks[k], ranks[k + 1]
+        cores.append(cores_buf[offs[k]: offs[k] + r0 * shape[k] * r1].view(r0, shape[k], r1))
+    if return_info:
+        return cores, dict(norm=info[0], eig_solves=int(info[1]), chfsi_products=int(info[2]), tc_grams=int(info[3]))
+    return cores
+
+
+class TTSVDPlan:
+    """Pre-allocated buffers for repeated decompositions of one shape (bench.py, serving loops)."""
+
+    def __init__(self, shape: Sequence[int], dtype: torch.dtype, rmax=None, device="cuda", use_tensorcore: bool = True,
+                 host_io: bool = False):
+        self.shape = [int(s) for s in shape]
+        self.N = len(self.shape)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.code = _DT[dtype]
+        self.rm = _rmax_list(rmax, max(self.N - 1, 0))
+        self.flags = 0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE
+        L = lib()
+        self._sh = i64(self.shape)
+        self._rm = i32(self.rm) if self.N > 1 else i32([0])
+        self._offs = (C.c_int64 * self.N)()
+        self.cap = L.tnb_ttsvd_cores_capacity(self.N, self._sh, self._rm, self._offs)
+        wsb = L.tnb_ttsvd_workspace_bytes(self.code, self.N, self._sh, self._rm, self.flags)
+        if self.cap < 0 or wsb == 0:
+            check(_lib.ERR_UNSUPPORTED)
+        self.ws = _ws(wsb, self.device)
+        self.cores_buf = torch.empty(int(self.cap), dtype=dtype, device=self.device)
+        self.ranks = (C.c_int32 * (self.N + 1))()
+        self.info = (C.c_double * 8)()
+        self.numel = 1
+        for s in self.shape:
+            self.numel *= s
+        self.dev_in = None
+        self.cores_host = None
+        if host_io:
+            self.dev_in = torch.empty(self.numel, dtype=dtype, device=self.device)
+            self.cores_host = torch.empty(int(self.cap), dtype=dtype, pin_memory=True)
+
+    def run(self, data: torch.Tensor, eps: float = 1e-14):
+        with torch.cuda.device(self.device):
+            check(lib().tnb_ttsvd(self.code, _ptr(data), self.N, self._sh, self._rm, float(eps), self.flags,
+                                  _ptr(self.ws), self.ws.numel(), _ptr(self.cores_buf), self.cap, self.ranks, self.info,
+                                  _stream()))
+        return self._views(self.cores_buf)
+
+    def run_host(self, data_host: torch.Tensor, eps: float = 1e-14):
+        """End-to-end call on HOST buffers: H2D of the tensor, decomposition, D2H of the cores."""
+        assert self.dev_in is not None, "construct the plan with host_io=True"
+        with torch.cuda.device(self.device):
+            check(lib().tnb_ttsvd_host(self.code, _ptr(data_host), self.N, self._sh, self._rm, float(eps), self.flags,
+                                       _ptr(self.dev_in), _ptr(self.ws), self.ws.numel(), _ptr(self.cores_buf), self.cap,
+                                       _ptr(self.cores_host), self.ranks, self.info, _stream()))
+        return self._views(self.cores_host)
+
+    def _views(self, buf):
+        out = []
+        for k in range(self.N):
+            r0, r1 = self.ranks[k], self.ranks[k + 1]
+            out.append(buf[self._offs[k]: self._offs[k] + r0 * self.shape[k] * r1].view(r0, self.shape[k], r1))
+        return out
+
+
+# --------------------------------------------------------------------------------------
+def tt_round(cores: Sequence[torch.Tensor], eps: float = 1e-14, rmax=None, batch_mode: bool = False):
+    """Tensor.round_tt on device cores (tensor.py:2008-2083). Returns new cores."""
+    N = len(cores)
+    for c in cores:
+        _require_cuda(c, "tt_round")
+        if c.dim() != 3:
+            raise ValueError("tt_round expects TT cores of shape [r, I, r']")
+    dt = cores[0].dtype
+    cores = [c.contiguous() for c in cores]
+    code = _dtype_code(cores[0])
+    shape = [c.shape[1] for c in cores]
+    rin = [cores[0].shape[0]] + [c.shape[2] for c in cores]
+    for k in range(N - 1):
+        if cores[k].shape[2] != cores[k + 1].shape[0]:
+            raise ValueError("Core ranks do not match")
+    rm = _rmax_list(rmax, max(N - 1, 0))
+    L = lib()
+    sh, rinc = i64(shape), i32(rin)
+    rmc = i32(rm) if N > 1 else i32([0])
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_tt_round_cores_capacity(N, sh, rinc, rmc, offs)
+    if cap < 0:
+        check(_lib.ERR_INVALID)
+    wsb = L.tnb_tt_round_workspace_bytes(code, N, sh, rinc, rmc)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    dev = cores[0].device
+    ws = _ws(wsb, dev)
+    out = torch.empty(int(cap), dtype=dt, device=dev)
+    ranks = (C.c_int32 * (N + 1))()
+    ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in cores])
+    flags = _lib.FLAG_BATCH_MODE if batch_mode else 0
+    with torch.cuda.device(dev):
+        check(L.tnb_tt_round(code, ptrs, N, sh, rinc, rmc, float(eps), flags, _ptr(ws), ws.numel(), _ptr(out), cap, ranks,
+                             _stream()))
+    res = []
+    for k in range(N):
+        r0, r1 = ranks[k], ranks[k + 1]
+        res.append(out[offs[k]: offs[k] + r0 * shape[k] * r1].view(r0, shape[k], r1))
+    return res
+
+
+def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tn.truncated_svd (round.py:52-187), non-batch."""
+    if delta is not None and eps is not None:
+        raise ValueError("Provide either `delta` or `eps`")
+    _require_cuda(M, "truncated_svd")
+    if M.dim() != 2:
+        raise ValueError("truncated_svd expects a matrix")
+    M = M.contiguous()
+    code = _dtype_code(M)
+    m, n = M.shape
+    if rmax is None:
+        rm = 0
+    else:
+        assert rmax >= 1
+        rm = int(min(rmax, 2**31 - 1))
+    L = lib()
+    wsb = L.tnb_truncated_svd_workspace_bytes(code, m, n)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, M.device)
+    k = min(m, n)
+    left = torch.empty(m * k, dtype=M.dtype, device=M.device)
+    right = torch.empty(k * n, dtype=M.dtype, device=M.device)
+    rank = (C.c_int32 * 1)()
+    with torch.cuda.device(M.device):
+        check(L.tnb_truncated_svd(code, _ptr(M), m, n, -1.0 if delta is None else float(delta),
+                                  -1.0 if eps is None else float(eps), rm, 1 if left_ortho else 0, _ptr(ws), ws.numel(),
+                                  _ptr(left), _ptr(right), rank, _stream()))
+    r = rank[0]
+    return left[: m * r].view(m, r), right[: r * n].view(r, n)
+
+
+def gram(A: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
+    """fp64 Gram matrix A^T A of a (rows x n) matrix; tensorcore=True uses the tcgen05/TMA kernel (fp32 only)."""
+    _require_cuda(A, "gram")
+    A = A.contiguous()
+    rows, n = A.shape
+    G = torch.empty(n, n, dtype=torch.float64, device=A.device)
+    L = lib()
+    with torch.cuda.device(A.device):
+        if tensorcore:
+            if A.dtype != torch.float32:
+                raise ValueError("tensor-core Gram needs float32 input")
+            wsb = L.tnb_gram_tc_workspace_bytes(rows, n)
+            if wsb == 0:
+                check(_lib.ERR_UNSUPPORTED)
+            ws = _ws(wsb, A.device)
+            check(L.tnb_gram_tc_f32(_ptr(A), rows, n, _ptr(G), _ptr(ws), ws.numel(), _stream()))
+        else:
+            code = _dtype_code(A)
+            ws = _ws(L.tnb_gram_workspace_bytes(code, rows, n), A.device)
+            check(L.tnb_gram(code, _ptr(A), rows, n, _ptr(G), _ptr(ws), ws.numel(), _stream()))
+    return G
+
+
+def project(A: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+    _require_cuda(A, "project")
+    A, V = A.contiguous(), V.contiguous()
+    rows, n = A.shape
+    assert V.shape[0] == n and V.dtype == A.dtype
+    r = V.shape[1]
+    Cc = torch.empty(rows, r, dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().tnb_project(_dtype_code(A), _ptr(A), rows, n, _ptr(V), r, _ptr(Cc), _stream()))
+    return Cc
+
+
+def eigh_jacobi(G: torch.Tensor):
+    _require_cuda(G, "eigh_jacobi")
+    G = G.contiguous().double()
+    n = G.shape[0]
+    w = torch.empty(n, dtype=torch.float64, device=G.device)
+    V = torch.empty(n, n, dtype=torch.float64, device=G.device)
+    L = lib()
+    wsb = L.tnb_eigh_workspace_bytes(n)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, G.device)
+    with torch.cuda.device(G.device):
+        check(L.tnb_eigh_jacobi(_ptr(G), n, _ptr(w), _ptr(V), _ptr(ws), ws.numel(), _stream()))
+    return w, V
+
+
+def eig_topk(G: torch.Tensor, k: int, b: int = 0, tol: float = 1e-6):
+    _require_cuda(G, "eig_topk")
+    G = G.contiguous().double()
+    n = G.shape[0]
+    L = lib()
+    wsb = L.tnb_eig_topk_workspace_bytes(n, k, b)
+    ws = _ws(wsb, G.device)
+    bb = b if b > 0 else min(n, min(256, max(2 * k, k + 16)))
+    w = torch.empty(bb, dtype=torch.float64, device=G.device)
+    V = torch.empty(n, bb, dtype=torch.float64, device=G.device)
+    info = (C.c_double * 4)()
+    with torch.cuda.device(G.device):
+        check(L.tnb_eig_topk(_ptr(G), n, k, b, float(tol), _ptr(w), _ptr(V), _ptr(ws), ws.numel(), info, _stream()))
+    return w, V, dict(products=int(info[0]), outer=int(info[1]), converged=int(info[2]))
+
+
+def tt_relative_error(data: torch.Tensor, cores: Sequence[torch.Tensor]) -> float:
+    """‖data − TT(cores)‖_F / ‖data‖_F, fp64 accumulation on the device (metrics.py:135-151)."""
+    _require_cuda(data, "tt_relative_error")
+    data = data.contiguous()
+    cores = [c.contiguous() for c in cores]
+    N = data.dim()
+    code = _dtype_code(data)
+    ranks = [cores[0].shape[0]] + [c.shape[2] for c in cores]
+    L = lib()
+    sh, rk = i64(list(data.shape)), i32(ranks)
+    wsb = L.tnb_tt_relative_error_workspace_bytes(code, N, sh, rk)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, data.device)
+    ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in cores])
+    res = (C.c_double * 1)()
+    with torch.cuda.device(data.device):
+        check(L.tnb_tt_relative_error(code, _ptr(data), ptrs, N, sh, rk, _ptr(ws), ws.numel(), res, _stream()))
+    return float(res[0])

@@ -1,0 +1,57 @@
+"""Module-level mirrors of tntorch/round.py:7-187 (clone-then-round wrappers, truncated_svd)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def round_tt(t, **kwargs):
+    """round.py:7-19"""
+    t2 = t.clone()
+    t2.round_tt(**kwargs)
+    return t2
+
+
+def round(t, **kwargs):
+    """round.py:37-49"""
+    t2 = t.clone()
+    t2.round(**kwargs)
+    return t2
+
+
+def truncated_svd(
+    M: torch.Tensor,
+    delta: Optional[float] = None,
+    eps: Optional[float] = None,
+    rmax: Optional[int] = None,
+    left_ortho: Optional[bool] = True,
+    algorithm: Optional[str] = "svd",
+    verbose: Optional[bool] = False,
+    batch: Optional[bool] = False,
+):
+    """round.py:52-187.  `algorithm` is accepted for signature parity; both values run the same
+    Gram + eigen kernels (the reference's own 'eig' formulation) with fp64 accumulation."""
+    if delta is not None and eps is not None:
+        raise ValueError("Provide either `delta` or `eps`")
+    assert rmax is None or rmax >= 1
+    assert algorithm in ("svd", "eig")
+    if batch:
+        # batch mode ignores eps/delta (round.py:149-150): rank = min(rmax, len(S))
+        outs = [ops.truncated_svd(M[b], rmax=min(rmax or min(M.shape[1:]), min(M.shape[1:])), left_ortho=left_ortho)
+                for b in range(M.shape[0])]
+        return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
+    return ops.truncated_svd(M, delta=delta, eps=eps, rmax=rmax, left_ortho=left_ortho)
+
+
+def relative_error(gt, approx):
+    """metrics.py:135-151 for (dense torch tensor, Tensor)."""
+    from .tensor import Tensor
+
+    if isinstance(gt, torch.Tensor) and isinstance(approx, Tensor) and not approx.batch:
+        return ops.tt_relative_error(gt.to(approx.cores[0].device), approx.cores)
+    a = gt.torch() if isinstance(gt, Tensor) else gt
+    b = approx.torch() if isinstance(approx, Tensor) else approx
+    return float(torch.dist(a, b) / torch.norm(a))
