@@ -40,6 +40,7 @@ extern "C" {
 /* flags for tnb_ttsvd / tnb_tt_round */
 #define TNB_FLAG_NO_TENSORCORE 1u /* force the generic fp32/fp64 CUDA-core kernels (debug / parity A-B) */
 #define TNB_FLAG_BATCH_MODE 2u    /* reference `batch=True` rank rule: rank = min(rmax, len(S)), no eps  */
+#define TNB_FLAG_PROFILE 4u       /* record CUDA events around each phase; timings returned in info_host  */
 
 int tnb_version(void);
 const char* tnb_last_error(void);
@@ -59,8 +60,9 @@ int tnb_has_tensorcore_path(void);
  *   cores      output buffer; core k is written at element offset core_offsets_host[k] with shape
  *              [ranks_host[k], shape[k], ranks_host[k+1]]; capacity from tnb_ttsvd_cores_capacity()
  *   ranks_host ndim+1 ints (host), ranks_host[0] = ranks_host[ndim] = 1
- *   info_host  optional (may be NULL) 8 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix
- *              products, [3]=#tensor-core Gram launches, [4..7] reserved
+ *   info_host  optional (may be NULL) 32 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix products,
+ *              [3]=#tensor-core Gram launches; with TNB_FLAG_PROFILE also [4]=Gram ms, [5]=eigen ms,
+ *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 8
  * ------------------------------------------------------------------------------------------ */
 int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host);
 size_t tnb_ttsvd_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* rmax, uint32_t flags);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libtnb200.so")
 TNB_F32, TNB_F64 = 0, 1
 FLAG_NO_TENSORCORE = 1
 FLAG_BATCH_MODE = 2
+FLAG_PROFILE = 4
 
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOCONV = 1, 2, 3, 4, 5
 

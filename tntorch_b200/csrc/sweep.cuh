@@ -174,6 +174,32 @@ struct SweepInfo {
   int eig_solves = 0;
   int chfsi_products = 0;
   int tc_grams = 0;
+  // TNB_FLAG_PROFILE: CUDA-event timings (ms) on the launching stream, per step (t = 0 is the first Gram)
+  int nsteps = 0;
+  double gram_ms[8] = {0}, eig_ms[8] = {0}, factor_ms[8] = {0};
+};
+
+// Event-based phase profiler (only active under TNB_FLAG_PROFILE; events are recorded on the stream the
+// kernels are launched on, and read after the per-step synchronisation the sweep performs anyway).
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  int used = 0;
+  cudaEvent_t next() {
+    if (used == (int)ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  void mark(cudaStream_t st) {
+    if (on) cudaEventRecord(next(), st);
+  }
+  static Prof& get() {
+    static thread_local Prof p;
+    return p;
+  }
 };
 
 struct StepCtx {
@@ -205,16 +231,20 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   T* fac = ar.template take<T>((size_t)L * (size_t)kcap);  // V_r or U_r/s
   if (dry) return TNB_OK;
   if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "workspace too small (need > %zu bytes)", ar.off);
+  Prof& prof = Prof::get();
+  prof.mark(st);
   int used_tc = 0;
   TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, cx.allow_tc, &used_tc, st));
   if (cx.info) cx.info->tc_grams += used_tc;
   trace_kernel<<<1, 256, 0, st>>>(G, (int)L, (int)L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
   TNB_LAUNCH_CHECK();
+  prof.mark(st);
   ChfsiStats cs;
   TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st));
   if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products;
   rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, cx.sc);
   TNB_LAUNCH_CHECK();
+  prof.mark(st);
   TNB_CUDA(cudaMemcpyAsync(cx.h_sc, cx.sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
   TNB_CUDA(cudaStreamSynchronize(st));
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(cx.h_sc);
@@ -244,6 +274,7 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
     scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, Cn, 2, 0);
     TNB_LAUNCH_CHECK();
   }
+  prof.mark(st);
   *rank_out = rank;
   return TNB_OK;
 }
@@ -263,6 +294,9 @@ inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, c
   const double epsN = eps / std::max(1.0, std::sqrt((double)(N - 1)));
   cx.eps_scaled2 = epsN * epsN;
   cx.sc = ar.template take<SweepScalars>(1);
+  Prof& prof = Prof::get();
+  prof.on = !dry && (flags & TNB_FLAG_PROFILE);
+  prof.used = 0;
   if (!dry) {
     cx.h_sc = static_cast<int*>(pinned_scratch(sizeof(SweepScalars)));
     if (!cx.h_sc) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
@@ -308,6 +342,20 @@ inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, c
     TNB_CUDA(cudaMemcpyAsync(cores + d.slot[0], C, sizeof(T) * (size_t)d.shape[0] * (size_t)r_next,
                              cudaMemcpyDeviceToDevice, st));
     TNB_CUDA(cudaStreamSynchronize(st));
+    if (prof.on && info) {  // 4 events per step: start, after Gram, after eigen+rank, after factor/projection
+      const int steps = prof.used / 4;
+      info->nsteps = steps;
+      for (int t = 0; t < steps && t < 8; ++t) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, prof.ev[4 * t], prof.ev[4 * t + 1]);
+        cudaEventElapsedTime(&b, prof.ev[4 * t + 1], prof.ev[4 * t + 2]);
+        cudaEventElapsedTime(&c, prof.ev[4 * t + 2], prof.ev[4 * t + 3]);
+        info->gram_ms[t] = a;
+        info->eig_ms[t] = b;
+        info->factor_ms[t] = c;
+      }
+    }
+    prof.on = false;
   }
   return TNB_OK;
 }

@@ -82,11 +82,20 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
     rc = ttsvd_impl<double>(ar, false, static_cast<const double*>(data), d, rmax, eps, flags,
                             static_cast<double*>(cores), ranks_host, &info, as_stream(stream));
   if (info_host) {
-    for (int i = 0; i < 8; ++i) info_host[i] = 0.0;
+    for (int i = 0; i < 32; ++i) info_host[i] = 0.0;
     info_host[0] = info.norm;
     info_host[1] = info.eig_solves;
     info_host[2] = info.chfsi_products;
     info_host[3] = info.tc_grams;
+    info_host[7] = info.nsteps;
+    for (int t = 0; t < info.nsteps && t < 8; ++t) {
+      info_host[4] += info.gram_ms[t];
+      info_host[5] += info.eig_ms[t];
+      info_host[6] += info.factor_ms[t];
+      info_host[8 + 3 * t] = info.gram_ms[t];
+      info_host[9 + 3 * t] = info.eig_ms[t];
+      info_host[10 + 3 * t] = info.factor_ms[t];
+    }
   }
   return rc;
 }

@@ -87,7 +87,7 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
     ws = _ws(wsb, data.device)
     cores_buf = torch.empty(int(cap), dtype=data.dtype, device=data.device)
     ranks = (C.c_int32 * (N + 1))()
-    info = (C.c_double * 8)()
+    info = (C.c_double * 32)()
     with torch.cuda.device(data.device):
         check(L.tnb_ttsvd(code, _ptr(data), N, sh, rmc, float(eps), flags, _ptr(ws), ws.numel(), _ptr(cores_buf), cap,
                           ranks, info, _stream()))
@@ -104,14 +104,14 @@ class TTSVDPlan:
     """Pre-allocated buffers for repeated decompositions of one shape (bench.py, serving loops)."""
 
     def __init__(self, shape: Sequence[int], dtype: torch.dtype, rmax=None, device="cuda", use_tensorcore: bool = True,
-                 host_io: bool = False):
+                 host_io: bool = False, profile: bool = False):
         self.shape = [int(s) for s in shape]
         self.N = len(self.shape)
         self.dtype = dtype
         self.device = torch.device(device)
         self.code = _DT[dtype]
         self.rm = _rmax_list(rmax, max(self.N - 1, 0))
-        self.flags = 0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE
+        self.flags = (0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_PROFILE if profile else 0)
         L = lib()
         self._sh = i64(self.shape)
         self._rm = i32(self.rm) if self.N > 1 else i32([0])
@@ -123,7 +123,7 @@ class TTSVDPlan:
         self.ws = _ws(wsb, self.device)
         self.cores_buf = torch.empty(int(self.cap), dtype=dtype, device=self.device)
         self.ranks = (C.c_int32 * (self.N + 1))()
-        self.info = (C.c_double * 8)()
+        self.info = (C.c_double * 32)()
         self.numel = 1
         for s in self.shape:
             self.numel *= s
