@@ -17,6 +17,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tnb {
@@ -41,6 +43,10 @@ struct GramTcParams {
   int64_t iters_per_split;
   float* partial;  // [ksplit][num_tiles][128][tn]
   int tmem_cols;
+  // shared-memory operand descriptor fields (see make_mn_major_desc)
+  uint32_t desc_layout;  // 1 = SWIZZLE_128B_BASE32B (the only MN-major layout tf32 operands accept)
+  uint32_t desc_lbo;     // bytes between 32-column groups (one TMA box)
+  uint32_t desc_sbo;     // bytes between K atoms (4 rows x 128 B)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -112,17 +118,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, MN-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
-//   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (stride between 32-column groups)
-//   bits [32,46) stride byte offset >> 4 (stride between 8-row groups = 1024 B)   bits [46,48) version = 1
-//   bits [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_mn_major_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor of an MN-major fp32/tf32 operand (cute::UMMA::SmemDescriptor bit layout):
+//   bits [0,14)  start address >> 4
+//   bits [16,30) leading byte offset >> 4  = stride between 32-column (128-byte) groups along M/N
+//   bits [32,46) stride byte offset >> 4   = stride between K atoms (4 rows of 128 B = 512 B)
+//   bits [46,48) version = 1 (Blackwell)     bits [61,64) layout type
+// tf32 MN-major operands only accept the "128-byte swizzle with 32-byte atoms" layout
+// (UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1; Swizzle<2,5,2>: the 32-byte chunk index is XORed with
+// row % 4), which is what the TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_mn_major_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32, both operands MN-major.
@@ -229,8 +240,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramTcParams p) {
         const uint32_t a_addr = a_in_b ? sb + (uint32_t)((a_col0 - b_col0) / 32) * TC_BOX_BYTES : sb + 8u * TC_BOX_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_KC / 8; ++ks) {
-          const uint64_t adesc = make_mn_major_desc(a_addr + ks * 1024u, TC_BOX_BYTES, 1024u);
-          const uint64_t bdesc = make_mn_major_desc(b_addr + ks * 1024u, TC_BOX_BYTES, 1024u);
+          const uint64_t adesc = make_mn_major_desc(a_addr + ks * 1024u, p.desc_lbo, p.desc_sbo, p.desc_layout);
+          const uint64_t bdesc = make_mn_major_desc(b_addr + ks * 1024u, p.desc_lbo, p.desc_sbo, p.desc_layout);
           tcgen05_mma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
         tcgen05_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
@@ -349,6 +360,15 @@ inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p) {
   while (cols < tn) cols <<= 1;
   p.tmem_cols = cols;
   p.partial = nullptr;
+  p.desc_layout = 1;
+  p.desc_lbo = TC_BOX_BYTES;
+  p.desc_sbo = 512;
+}
+
+// Debug-only: TNB_TC_VARIANT selects alternative descriptor encodings (bring-up A/B on the GPU box).
+inline int tc_variant() {
+  const char* e = getenv("TNB_TC_VARIANT");
+  return e ? atoi(e) : 0;
 }
 
 inline size_t gram_tc_workspace_bytes(int64_t rows, int64_t n) {
@@ -369,13 +389,20 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
   if (ws_bytes < need) return fail(TNB_ERR_WORKSPACE, "gram_tc: workspace %zu < %zu", ws_bytes, need);
   p.partial = static_cast<float*>(ws);
 
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  switch (tc_variant()) {
+    case 1: p.desc_lbo = 512; p.desc_sbo = TC_BOX_BYTES; break;                       // LBO/SBO swapped
+    case 2: p.desc_layout = 2; p.desc_sbo = 1024; swz = CU_TENSOR_MAP_SWIZZLE_128B; break;  // 16-byte-atom swizzle
+    case 3: p.desc_sbo = 1024; break;
+    default: break;
+  }
   CUtensorMap tmap;
   cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
   cuuint32_t box[2] = {32, (cuuint32_t)TC_KC};
   cuuint32_t estr[2] = {1, 1};
   CUresult cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(TNB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
