@@ -10,4 +10,4 @@ timeout 900 python -m pytest tests/test_gpu_ttsvd.py tests/test_gpu_round.py -m 
 timeout 600 python scripts/gpu_diag.py blocks > gpurun_out/d_blocks.log 2>&1
 timeout 900 python scripts/gpu_diag.py ttsvd > gpurun_out/d_ttsvd.log 2>&1; echo "diag ttsvd rc=$?"
 timeout 900 python scripts/gpu_diag.py big > gpurun_out/d_big.log 2>&1; echo "diag big rc=$?"
-tail -5 gpurun_out/t_blocks.log gpurun_out/t_tc.log gpurun_out/t_ttsvd.log; tail -20 gpurun_out/d_tc.log gpurun_out/d_big.log
+for f in t_blocks t_tc t_ttsvd; do tail -n 5 gpurun_out/$f.log; done; tail -n 20 gpurun_out/d_tc.log; tail -n 20 gpurun_out/d_big.log

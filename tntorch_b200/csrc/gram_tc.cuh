@@ -1,6 +1,6 @@
 // Gram matrix G = C^T C of a tall row-major fp32 matrix C (rows x n) on the Blackwell tensor cores.
 //
-//   * row slabs of C are staged HBM -> shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle,
+//   * row slabs of C are staged HBM -> shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle with 32-byte atoms,
 //     out-of-bounds rows/columns zero-filled by the TMA unit), 4-stage mbarrier ring;
 //   * the contraction runs over the ROW index of C, so both MMA operands are "MN-major" views of the
 //     very same slab: tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = TN <= 256, K = 8 per instruction,
@@ -365,12 +365,6 @@ inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p) {
   p.desc_sbo = 512;
 }
 
-// Debug-only: TNB_TC_VARIANT selects alternative descriptor encodings (bring-up A/B on the GPU box).
-inline int tc_variant() {
-  const char* e = getenv("TNB_TC_VARIANT");
-  return e ? atoi(e) : 0;
-}
-
 inline size_t gram_tc_workspace_bytes(int64_t rows, int64_t n) {
   GramTcParams p;
   gram_tc_plan(rows, n, p);
@@ -389,13 +383,7 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
   if (ws_bytes < need) return fail(TNB_ERR_WORKSPACE, "gram_tc: workspace %zu < %zu", ws_bytes, need);
   p.partial = static_cast<float*>(ws);
 
-  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  switch (tc_variant()) {
-    case 1: p.desc_lbo = 512; p.desc_sbo = TC_BOX_BYTES; break;                       // LBO/SBO swapped
-    case 2: p.desc_layout = 2; p.desc_sbo = 1024; swz = CU_TENSOR_MAP_SWIZZLE_128B; break;  // 16-byte-atom swizzle
-    case 3: p.desc_sbo = 1024; break;
-    default: break;
-  }
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;  // matches UMMA SWIZZLE_128B_BASE32B
   CUtensorMap tmap;
   cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
