@@ -163,7 +163,7 @@ inline GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, bool symmetric, int f
   if (tiles < 1) tiles = 1;
   int sms = device_info().valid ? device_info().sm_count : 148;
   int64_t want = ceil_div<int64_t>(2 * (int64_t)sms * 2, tiles);  // 2 CTAs/SM resident, 2 waves
-  int64_t max_by_k = K / 256 > 0 ? K / 256 : 1;
+  int64_t max_by_k = K / 64 > 0 ? K / 64 : 1;
   int64_t s = want < max_by_k ? want : max_by_k;
   if (s < 1) s = 1;
   if (s > 64) s = 64;

@@ -1,5 +1,5 @@
-// Small dense symmetric eigenproblems on one CTA: parallel-order two-sided Jacobi with
-// warp/block reductions, fp64 throughout.  Replaces torch.linalg.eigh (round.py:114) and the
+// Small dense symmetric eigenproblems on one CTA: parallel-order one-sided (Hestenes) Jacobi with
+// warp-shuffle reductions, fp64 throughout.  Replaces torch.linalg.eigh (round.py:114) and the
 // U,S part of torch.linalg.svd (round.py:96) for Gram matrices up to JACOBI_MAX_N.
 #pragma once
 #include "common.cuh"
@@ -28,7 +28,11 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red /*>=32 
   return out;
 }
 
-// Eigen-decomposition of the symmetric n x n matrix Gin (leading dimension ldg).
+// Eigen-decomposition of the symmetric PSD n x n matrix Gin (leading dimension ldg) by ONE-SIDED
+// (Hestenes) Jacobi: W = G V is kept column by column; each warp owns one column pair per round,
+// takes the three inner products with shuffle reductions, rotates its two columns of W and V, and the
+// only block-wide synchronisation is one barrier per round (np-1 rounds per sweep, circle ordering).
+// At convergence the columns of W are orthogonal: W = V diag(lambda), lambda_c = v_c . w_c.
 //   w_out[0..n)   eigenvalues, descending
 //   V_out[n x n]  row-major, column j = eigenvector of w_out[j]
 //   scratch       2*np*np doubles when !SMEM (np = n rounded up to even)
@@ -42,96 +46,100 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   extern __shared__ __align__(16) unsigned char jac_smem_raw[];
   const int np = n + (n & 1);
   const int m = np >> 1;
-  double* A;
-  double* V;
+  double* Wt;  // column-major: Wt[c*np + r] = W[r][c]
+  double* Vt;
   if (SMEM) {
-    A = reinterpret_cast<double*>(jac_smem_raw);
-    V = A + (size_t)np * np;
+    Wt = reinterpret_cast<double*>(jac_smem_raw);
+    Vt = Wt + (size_t)np * np;
   } else {
-    A = scratch;
-    V = scratch + (size_t)np * np;
+    Wt = scratch;
+    Vt = scratch + (size_t)np * np;
   }
-  __shared__ double s_c[JACOBI_MAX_N / 2 + 1], s_s[JACOBI_MAX_N / 2 + 1];
-  __shared__ int s_p[JACOBI_MAX_N / 2 + 1], s_q[JACOBI_MAX_N / 2 + 1];
-  __shared__ double s_red[32];
   __shared__ double s_w[JACOBI_MAX_N + 2];
   __shared__ int s_rank[JACOBI_MAX_N + 2];
+  __shared__ double s_gmax;
+  __shared__ int s_nrot;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
   for (int idx = tid; idx < np * np; idx += nt) {
-    const int i = idx / np, j = idx % np;
+    const int c = idx / np, r = idx % np;
     double v = 0.0;
-    if (i < n && j < n) v = 0.5 * (Gin[(size_t)i * ldg + j] + Gin[(size_t)j * ldg + i]);  // symmetrise
-    A[idx] = v;
-    V[idx] = (i == j) ? 1.0 : 0.0;
+    if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]);  // symmetrise
+    Wt[idx] = v;
+    Vt[idx] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
+  // scale reference: largest squared column norm (~ lambda_max^2)
+  for (int c = warp; c < np; c += nwarps) {
+    double s = 0.0;
+    for (int r = lane; r < np; r += 32) { const double a = Wt[(size_t)c * np + r]; s += a * a; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_w[c] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double g = 0.0;
+    for (int c = 0; c < np; ++c) g = s_w[c] > g ? s_w[c] : g;
+    s_gmax = g;
+  }
+  __syncthreads();
+  const double floor2 = 1e-30 * s_gmax;  // pairs of columns both at the noise level are left alone
 
-  __shared__ int s_nrot;
   int sweeps_done = 0;
   bool converged = false;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (tid == 0) s_nrot = 0;
     __syncthreads();
+    int rot = 0;
     for (int step = 0; step < np - 1; ++step) {
-      // phase 1: the m disjoint pairs of this round (circle method) and their rotations
-      if (tid < m) {
+      for (int pi = warp; pi < m; pi += nwarps) {
         int p, q;
-        if (tid == 0) {
+        if (pi == 0) {
           p = np - 1;
           q = step % (np - 1);
         } else {
-          p = (step + tid) % (np - 1);
-          q = (step - tid + (np - 1)) % (np - 1);
+          p = (step + pi) % (np - 1);
+          q = (step - pi + (np - 1)) % (np - 1);
         }
         if (p > q) { const int t = p; p = q; q = t; }
-        const double app = A[(size_t)p * np + p], aqq = A[(size_t)q * np + q], apq = A[(size_t)p * np + q];
-        double c = 1.0, s = 0.0;
-        // relative (Demmel-Veselic) rotation threshold: keeps small eigenvalues of PSD matrices accurate
-        if (fabs(apq) > tol * sqrt(fabs(app * aqq)) && fabs(apq) > 1e-290) {
-          atomicAdd(&s_nrot, 1);
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
-          s = t * c;
+        double* wp = Wt + (size_t)p * np;
+        double* wq = Wt + (size_t)q * np;
+        double dpp = 0.0, dqq = 0.0, dpq = 0.0;
+        for (int r = lane; r < np; r += 32) {
+          const double a = wp[r], b = wq[r];
+          dpp = fma(a, a, dpp);
+          dqq = fma(b, b, dqq);
+          dpq = fma(a, b, dpq);
         }
-        s_p[tid] = p; s_q[tid] = q; s_c[tid] = c; s_s[tid] = s;
-      }
-      __syncthreads();
-      // phase 2: A <- A J, V <- V J  (columns p,q of every row)
-      for (int idx = tid; idx < m * np; idx += nt) {
-        const int i = idx % m, k = idx / m;
-        const double c = s_c[i], s = s_s[i];
-        if (s == 0.0) continue;
-        const int p = s_p[i], q = s_q[i];
-        const size_t kp = (size_t)k * np + p, kq = (size_t)k * np + q;
-        const double a1 = A[kp], a2 = A[kq];
-        A[kp] = c * a1 - s * a2;
-        A[kq] = s * a1 + c * a2;
-        const double v1 = V[kp], v2 = V[kq];
-        V[kp] = c * v1 - s * v2;
-        V[kq] = s * v1 + c * v2;
-      }
-      __syncthreads();
-      // phase 3: A <- J^T A  (rows p,q across every column)
-      for (int idx = tid; idx < m * np; idx += nt) {
-        const int i = idx / np, k = idx % np;
-        const double c = s_c[i], s = s_s[i];
-        if (s == 0.0) continue;
-        const int p = s_p[i], q = s_q[i];
-        const size_t pk = (size_t)p * np + k, qk = (size_t)q * np + k;
-        const double a1 = A[pk], a2 = A[qk];
-        A[pk] = c * a1 - s * a2;
-        A[qk] = s * a1 + c * a2;
-      }
-      __syncthreads();
-      if (tid < m && s_s[tid] != 0.0) {  // the annihilated pair: exact zeros, symmetric
-        const int p = s_p[tid], q = s_q[tid];
-        A[(size_t)p * np + q] = 0.0;
-        A[(size_t)q * np + p] = 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+          dpp += __shfl_xor_sync(0xffffffffu, dpp, o);
+          dqq += __shfl_xor_sync(0xffffffffu, dqq, o);
+          dpq += __shfl_xor_sync(0xffffffffu, dpq, o);
+        }
+        const double scale = sqrt(dpp * dqq);
+        if (fabs(dpq) > tol * scale && scale > floor2) {  // warp-uniform
+          rot = 1;
+          const double tau = (dqq - dpp) / (2.0 * dpq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double c = 1.0 / sqrt(1.0 + t * t);
+          const double s = t * c;
+          double* vp = Vt + (size_t)p * np;
+          double* vq = Vt + (size_t)q * np;
+          for (int r = lane; r < np; r += 32) {
+            const double a = wp[r], b = wq[r];
+            wp[r] = c * a - s * b;
+            wq[r] = s * a + c * b;
+            const double x = vp[r], y = vq[r];
+            vp[r] = c * x - s * y;
+            vq[r] = s * x + c * y;
+          }
+        }
       }
       __syncthreads();
     }
+    if (lane == 0 && rot) atomicAdd(&s_nrot, 1);
+    __syncthreads();
     sweeps_done = sweep + 1;
     const int nrot = s_nrot;
     __syncthreads();
@@ -141,8 +149,13 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
     }
   }
 
-  // sort descending (rank by counting), write out
-  for (int i = tid; i < n; i += nt) s_w[i] = A[(size_t)i * np + i];
+  // eigenvalues as Rayleigh quotients lambda_c = v_c . (G v_c) = v_c . w_c ; sort descending; write out
+  for (int c = warp; c < n; c += nwarps) {
+    double s = 0.0;
+    for (int r = lane; r < np; r += 32) s = fma(Vt[(size_t)c * np + r], Wt[(size_t)c * np + r], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_w[c] = s;
+  }
   __syncthreads();
   for (int i = tid; i < n; i += nt) {
     const double wi = s_w[i];
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += nt) {
     const int k = idx / n, i = idx % n;
-    V_out[(size_t)k * n + s_rank[i]] = V[(size_t)k * np + i];
+    V_out[(size_t)k * n + s_rank[i]] = Vt[(size_t)i * np + k];
   }
   if (tid == 0 && info) info[0] = converged ? sweeps_done : -sweeps_done;
 }

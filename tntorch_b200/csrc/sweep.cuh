@@ -18,10 +18,21 @@
 #include "jacobi.cuh"
 #include "small_kernels.cuh"
 #include "gram_tc.cuh"
+#include "project.cuh"
 
 namespace tnb {
 
-constexpr int64_t TC_MIN_ROWS = 8192;  // below this the generic fp64-accumulating Gram is used
+// C (rows x r) = A (rows x n) * V (n x r) in the data precision: streaming FFMA kernel for fp32 when the
+// shape allows, generic tiled GEMM otherwise.
+template <typename T>
+inline int project_any(const T* A, int64_t rows, int64_t n, const T* V, int64_t r, T* C, cudaStream_t st) {
+  if (std::is_same<T, float>::value && project_f32_fast_ok(rows, n, r, A, C))
+    return project_f32_fast(reinterpret_cast<const float*>(A), rows, n, reinterpret_cast<const float*>(V), (int)r,
+                            reinterpret_cast<float*>(C), st);
+  return gemm_direct<T, T, T, T>(rows, r, n, A, n, true, V, r, false, C, r, (T)1, nullptr, 0, (T)0, nullptr, 0, (T)0, st);
+}
+
+constexpr int64_t TC_MIN_ROWS = 2048;  // below this the generic fp64-accumulating Gram is used
 
 struct SweepDims {
   int N = 0;
@@ -263,8 +274,7 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
     TNB_LAUNCH_CHECK();
     scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)n, (int)rank, ew.w, fac, 0, 0);
     TNB_LAUNCH_CHECK();
-    TNB_TRY((gemm_direct<T, T, T, T>(rows, rank, n, C, n, true, fac, rank, false, Cn, rank, (T)1, nullptr, 0, (T)0,
-                                     nullptr, 0, (T)0, st)));
+    TNB_TRY(project_any<T>(C, rows, n, fac, rank, Cn, st));
   } else {
     // core = diag(1/s) U_r^T C (rank x n);  Cn = U_r diag(s)
     scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, fac, 1, 0);

@@ -245,12 +245,10 @@ int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V
   if (!A || !V || !C || rows < 1 || n < 1 || r < 1) return fail(TNB_ERR_INVALID, "tnb_project: bad argument");
   cudaStream_t st = as_stream(stream);
   if (dtype == TNB_F32)
-    return gemm_direct<float, float, float, float>(rows, r, n, static_cast<const float*>(A), n, true,
-                                                   static_cast<const float*>(V), r, false, static_cast<float*>(C), r, 1.f,
-                                                   nullptr, 0, 0.f, nullptr, 0, 0.f, st);
-  return gemm_direct<double, double, double, double>(rows, r, n, static_cast<const double*>(A), n, true,
-                                                     static_cast<const double*>(V), r, false, static_cast<double*>(C), r,
-                                                     1.0, nullptr, 0, 0.0, nullptr, 0, 0.0, st);
+    return project_any<float>(static_cast<const float*>(A), rows, n, static_cast<const float*>(V), r,
+                              static_cast<float*>(C), st);
+  return project_any<double>(static_cast<const double*>(A), rows, n, static_cast<const double*>(V), r,
+                             static_cast<double*>(C), st);
 }
 
 size_t tnb_eigh_workspace_bytes(int32_t n) {

@@ -1,0 +1,65 @@
+"""Batch sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+The path shards over independent tensors: rank g decomposes the contiguous slice of the batch it
+owns with no data-path collective; ONE all-gather at the end gives every rank all factor cores
+(BASELINE.json north_star).  Works on any backend (NCCL on the GPUs, gloo in the
+CPU test-suite, where only the plumbing is exercised).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch: int, world: int, rank: int):
+    """Contiguous chunk [lo, hi) of a batch of `batch` problems owned by `rank` (ragged tail spread evenly)."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def all_gather_cores(local: Sequence[Sequence[torch.Tensor]], batch: int) -> List[List[torch.Tensor]]:
+    """local: for each locally-owned problem, its list of TT cores.  Returns the cores of all `batch`
+    problems on every rank.  Ranks are data dependent (eps-driven), so shapes are gathered first, then one
+    flat all-gather moves the payload (padded to the largest shard)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [list(c) for c in local]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = local[0][0].device if len(local) else torch.device("cpu")
+    dtype = local[0][0].dtype if len(local) else torch.float32
+    meta = [[list(c.shape) for c in cores] for cores in local]
+    metas = [None] * world
+    dist.all_gather_object(metas, meta)
+    flat = torch.cat([c.reshape(-1) for cores in local for c in cores]) if len(local) else torch.empty(0, dtype=dtype, device=dev)
+    sizes = [sum(int(torch.Size(s).numel()) for cores in m for s in cores) for m in metas]
+    pad = max(sizes) if sizes else 0
+    buf = torch.zeros(pad, dtype=dtype, device=dev)
+    buf[: flat.numel()] = flat
+    out = [torch.empty(pad, dtype=dtype, device=dev) for _ in range(world)]
+    dist.all_gather(out, buf)
+    result: List[List[torch.Tensor]] = []
+    for g in range(world):
+        off = 0
+        for cores in metas[g]:
+            cur = []
+            for s in cores:
+                n = int(torch.Size(s).numel())
+                cur.append(out[g][off: off + n].view(*s))
+                off += n
+            result.append(cur)
+    assert len(result) == batch, (len(result), batch)
+    return result
+
+
+def ttsvd_batch_sharded(tensors: Sequence[torch.Tensor], rmax=None, eps: float = 1e-14, gather: bool = True):
+    """Decompose a batch of dense tensors, sharded over the ranks of the default process group."""
+    from . import ops
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(len(tensors), world, rank)
+    local = [ops.ttsvd(tensors[i], rmax=rmax, eps=eps) for i in range(lo, hi)]
+    return all_gather_cores(local, len(tensors)) if gather else local
