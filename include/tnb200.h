@@ -117,6 +117,12 @@ int tnb_gram(int dtype, const void* A, int64_t rows, int64_t n, double* G, void*
 size_t tnb_gram_tc_workspace_bytes(int64_t rows, int64_t n);
 int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
                     void* stream);
+/* C (m x n) = alpha * A^T B + beta * D on the same tcgen05 kernel (A: K x m, B: K x n, row-major fp32, TF32
+ * operands, fp32 accumulation; m, n multiples of 4, >= 32).  The Chebyshev-filter products G*Y of
+ * tnb_eig_topk's subspace iteration run through this entry (G symmetric => A = G).  D may be NULL. */
+size_t tnb_atb_tc_workspace_bytes(int64_t K, int64_t m, int64_t n);
+int tnb_atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t n, float* C, float alpha,
+                   const float* D, float beta, void* workspace, size_t workspace_bytes, void* stream);
 /* C (rows x r) = A (rows x n) * V (n x r), same dtype throughout (fp32: FFMA, fp32 accumulate).
  * Replaces: `M @ left` round.py:181 / einsum absorb tensor.py:2081-2083. */
 int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream);

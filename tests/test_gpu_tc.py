@@ -39,3 +39,24 @@ def test_gram_tc_structured_exact():
     G = ops.gram(A, tensorcore=True)
     ref = A.double().T @ A.double()
     assert torch.equal(G, ref)
+
+
+@pytest.mark.parametrize("shape", [(2048, 2048, 64), (1000, 300, 36), (4096, 128, 256), (777, 2048, 128)])
+def test_atb_tc_matches_fp64(shape):
+    """General A^T B on the tensor cores (the subspace-iteration filter product) incl. the fused epilogue."""
+    from tntorch_b200 import ops
+
+    K, m, n = shape
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(K, m, generator=g).cuda()
+    B = torch.randn(K, n, generator=g).cuda()
+    D = torch.randn(m, n, generator=g).cuda()
+    C = ops.atb_tensorcore(A, B, alpha=0.5, D=D, beta=-2.0)
+    ref = 0.5 * (A.double().T @ B.double()) - 2.0 * D.double()
+    err = (C.double() - ref).abs().max().item() / (A.double().T @ B.double()).abs().max().item()
+    assert err < 3e-3, err
+    # exact on TF32-representable integers
+    Ai = torch.randint(-8, 9, (K, m), generator=g).float().cuda()
+    Bi = torch.randint(-8, 9, (K, n), generator=g).float().cuda()
+    Ci = ops.atb_tensorcore(Ai, Bi)
+    assert torch.equal(Ci.double(), Ai.double().T @ Bi.double())

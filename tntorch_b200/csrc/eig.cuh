@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_generic.cuh"
+#include "gram_tc.cuh"
 #include "jacobi.cuh"
 #include "small_kernels.cuh"
 
@@ -33,6 +34,7 @@ struct ChfsiWork {
   TB* Tm;                   // b x b
   void* partial;            // split-K scratch, partial_bytes
   size_t partial_bytes;
+  bool use_tc = false;      // filter products on the tcgen05 kernel (fp32 blocks only)
   double *S, *lam, *Q, *d;  // b*b, b, b*b, b
   double* jscratch;         // jacobi_scratch_doubles(b)
   int* jinfo;
@@ -51,6 +53,10 @@ inline void chfsi_carve(ArenaT& ar, int n, int b, ChfsiWork<TB>& w) {
   GemmPlan p2 = plan_gemm(b, b, n, false);
   size_t e1 = p1.partial_elems * sizeof(TB), e2 = p2.partial_elems * sizeof(double);
   w.partial_bytes = e1 > e2 ? e1 : e2;
+  if (std::is_same<TB, float>::value && atb_tc_shape_ok(n, n, b)) {
+    const size_t e3 = atb_tc_workspace_bytes(n, n, b);
+    if (e3 > w.partial_bytes) w.partial_bytes = e3;
+  }
   w.partial = ar.template take<char>(w.partial_bytes);
   w.S = ar.template take<double>((size_t)b * b);
   w.lam = ar.template take<double>(b);
@@ -61,9 +67,17 @@ inline void chfsi_carve(ArenaT& ar, int n, int b, ChfsiWork<TB>& w) {
 }
 
 // Y <- a * G*Yin + bc * Yin + g * Xin      (G symmetric, stored n x n in TB)
+// tensorcore = true routes the product through the tcgen05 kernel (TF32 operands): used for the Chebyshev
+// FILTER only, where operator accuracy merely affects the convergence rate; the Rayleigh-Ritz product stays
+// fp32 FFMA so that the projected matrix, and with it the captured energy, is exact to fp32.
 template <typename TB>
 inline int chfsi_apply(const TB* G, int n, int b, const TB* Yin, const TB* Xin, TB* Yout, double a, double bc, double g,
-                       ChfsiWork<TB>& w, cudaStream_t st) {
+                       ChfsiWork<TB>& w, cudaStream_t st, bool tensorcore = false) {
+  if (tensorcore && w.use_tc && std::is_same<TB, float>::value)
+    return atb_tc_f32(reinterpret_cast<const float*>(G), n, n, reinterpret_cast<const float*>(Yin), b,
+                      reinterpret_cast<float*>(Yout), b, (float)a, (bc != 0.0 ? reinterpret_cast<const float*>(Yin) : nullptr),
+                      b, (float)bc, (g != 0.0 ? reinterpret_cast<const float*>(Xin) : nullptr), b, (float)g, w.partial,
+                      w.partial_bytes, st);
   GemmPlan pl = plan_gemm(n, b, n, false);
   return gemm_splitk<TB, TB, TB, TB, TB>(pl, n, b, n, G, n, /*a_kmaj (symmetric: either)*/ false, Yin, b, false,
                                          reinterpret_cast<TB*>(w.partial), Yout, b, (TB)a, (bc != 0.0 ? Yin : nullptr), b,
@@ -81,8 +95,9 @@ inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>
                                                          0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
     svqb_prep_kernel<<<1, 1024, 0, st>>>(w.S, b, w.d);
     TNB_LAUNCH_CHECK();
-    TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st));
-    svqb_finish_kernel<TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.lam, w.d, b, 1e-13, w.Tm);
+    TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value));
+    svqb_finish_kernel<TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.lam, w.d, b,
+                                                                     std::is_same<TB, float>::value ? 1e-6 : 1e-13, w.Tm);
     TNB_LAUNCH_CHECK();
     TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,
                                          nullptr, 0, (TB)0, st)));
@@ -99,7 +114,7 @@ inline int chfsi_rayleigh_ritz(const TB* G, int n, int b, TB** Xio, TB** Xtmp, C
   TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, w.W, b, false,
                                                        reinterpret_cast<double*>(w.partial), w.S, b, 1.0, nullptr, 0,
                                                        0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
-  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st));
+  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value));
   convert_kernel<double, TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.Tm, (int64_t)b * b);
   TNB_LAUNCH_CHECK();
   TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,
@@ -120,6 +135,8 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
   if (!h_theta) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
   const int max_outer = 40, mmax = 40;
   const double spread = 1e4;
+  w.use_tc = w.use_tc && std::is_same<TB, float>::value && tc_path_available() && atb_tc_shape_ok(n, n, b) &&
+             (reinterpret_cast<uintptr_t>(G) & 15u) == 0;
 
   random_fill_kernel<TB><<<grid_for((int64_t)n * b), 256, 0, st>>>(w.X, (int64_t)n * b, 0x1234567u);
   TNB_LAUNCH_CHECK();
@@ -172,13 +189,13 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
         if (all3[q] != X) bufs[c3++] = all3[q];
     }
     // Y = (G X - c X) * sigma1/e
-    TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[0], nullptr, bufs[1], sigma1 / e, -c * sigma1 / e, 0.0, w, st));
+    TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[0], nullptr, bufs[1], sigma1 / e, -c * sigma1 / e, 0.0, w, st, true));
     int iprev = 0, icur = 1, inew = 2;
     for (int i = 2; i <= m; ++i) {
       const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
       // Ynew = 2 sigma2/e (G Y - c Y) - sigma sigma2 Xprev
       TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[icur], bufs[iprev], bufs[inew], 2.0 * sigma2 / e, -2.0 * sigma2 * c / e,
-                              -sigma * sigma2, w, st));
+                              -sigma * sigma2, w, st, true));
       const int t = iprev; iprev = icur; icur = inew; inew = t;
       sigma = sigma2;
     }

@@ -32,10 +32,12 @@ constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GramTcParams {
-  int64_t rows;
-  int n;
+  int64_t rows;    // contraction length K (rows of both operands)
+  int n;           // columns of B (= of A in the symmetric Gram case)
+  int m;           // columns of A
+  int symmetric;   // 1: A == B, only tiles touching the upper triangle; 0: general A^T B
   int tn;          // B tile width (multiple of 32, <= 256)
-  int num_bm;      // ceil(n / 128)
+  int num_bm;      // ceil(m / 128)
   int num_bn;      // ceil(n / tn)
   int num_tiles;   // kept tiles
   int ksplit;
@@ -153,7 +155,8 @@ __host__ __device__ inline uint32_t make_idesc_tf32_mn(int M, int N) {
 // The kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramTcParams p) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+               const GramTcParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte aligned stage buffers (SWIZZLE_128B atoms are 1024 B)
   const uint32_t raw_addr = smem_u32(tc_smem_raw);
@@ -172,12 +175,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramTcParams p) {
   if (threadIdx.x == 0) {
     // flat tile id -> (bm, bn) among the tiles that touch the upper triangle
     int cnt = 0, fbm = 0, fbn = 0;
-    for (int bm = 0; bm < p.num_bm; ++bm)
-      for (int bn = 0; bn < p.num_bn; ++bn)
-        if ((bn + 1) * p.tn > bm * 128) {
-          if (cnt == tile_id) { fbm = bm; fbn = bn; }
-          ++cnt;
-        }
+    if (p.symmetric) {
+      for (int bm = 0; bm < p.num_bm; ++bm)
+        for (int bn = 0; bn < p.num_bn; ++bn)
+          if ((bn + 1) * p.tn > bm * 128) {
+            if (cnt == tile_id) { fbm = bm; fbn = bn; }
+            ++cnt;
+          }
+    } else {
+      fbm = tile_id / p.num_bn;
+      fbn = tile_id % p.num_bn;
+    }
     tile_smem[0] = fbm;
     tile_smem[1] = fbn;
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -201,7 +209,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramTcParams p) {
   const int bm = tile_smem[0], bn = tile_smem[1];
   const int a_col0 = bm * 128, b_col0 = bn * p.tn;
   const int nbox_b = p.tn / 32;
-  const bool a_in_b = (a_col0 >= b_col0) && (a_col0 + 128 <= b_col0 + p.tn);
+  const bool a_in_b = p.symmetric && (a_col0 >= b_col0) && (a_col0 + 128 <= b_col0 + p.tn);
   const int nbox_a = a_in_b ? 0 : 4;
   const int64_t it_begin = (int64_t)split * p.iters_per_split;
   int64_t it_end = it_begin + p.iters_per_split;
@@ -220,7 +228,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramTcParams p) {
         mbar_expect_tx(&full_bar[stage], tx_bytes);
         const int row0 = (int)((it_begin + it) * TC_KC);
         // B boxes first (slots 0..nbox_b), then A boxes (slots 8..11)
-        for (int j = 0; j < nbox_b; ++j) tma_load_2d(sb + j * TC_BOX_BYTES, &tmap, &full_bar[stage], b_col0 + 32 * j, row0);
+        for (int j = 0; j < nbox_b; ++j) tma_load_2d(sb + j * TC_BOX_BYTES, &tmap_b, &full_bar[stage], b_col0 + 32 * j, row0);
         for (int j = 0; j < nbox_a; ++j)
           tma_load_2d(sb + (8 + j) * TC_BOX_BYTES, &tmap, &full_bar[stage], a_col0 + 32 * j, row0);
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -336,17 +344,23 @@ inline bool gram_tc_shape_ok(int64_t rows, int64_t n) {
   return n >= 16 && n % 4 == 0 && n <= 16384 && rows >= 1 && rows < ((int64_t)1 << 31) - 64;
 }
 
-inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p) {
+inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p, int64_t m_cols = -1) {
   p.rows = rows;
   p.n = (int)n;
+  p.symmetric = m_cols < 0 ? 1 : 0;
+  p.m = p.symmetric ? (int)n : (int)m_cols;
   int tn = n >= 256 ? 256 : (int)((n + 31) / 32 * 32);
   p.tn = tn;
-  p.num_bm = (int)((n + 127) / 128);
+  p.num_bm = (int)((p.m + 127) / 128);
   p.num_bn = (int)((n + tn - 1) / tn);
   int cnt = 0;
-  for (int bm = 0; bm < p.num_bm; ++bm)
-    for (int bn = 0; bn < p.num_bn; ++bn)
-      if ((bn + 1) * tn > bm * 128) ++cnt;
+  if (p.symmetric) {
+    for (int bm = 0; bm < p.num_bm; ++bm)
+      for (int bn = 0; bn < p.num_bn; ++bn)
+        if ((bn + 1) * tn > bm * 128) ++cnt;
+  } else {
+    cnt = p.num_bm * p.num_bn;
+  }
   p.num_tiles = cnt;
   p.iters_total = (rows + TC_KC - 1) / TC_KC;
   int sms = device_info().valid ? device_info().sm_count : 148;
@@ -400,10 +414,86 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
     attr_set = true;
   }
   dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
-  gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, p);
+  gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, tmap, p);
   TNB_LAUNCH_CHECK();
   const int64_t total = n * n;
   gram_tc_finalize_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(p, G, Gf);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General C (m x n) = alpha * A^T B + beta * D + gamma * E on the same kernel: A is K x m, B is K x n,
+// both row-major fp32 (TF32 operands, fp32 accumulation).  Used for the filter products G*Y of the
+// subspace iteration (G symmetric, so A = G).  Finalize fuses the three-term epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void atb_tc_finalize_kernel(const GramTcParams p, float* __restrict__ C, int ldc, float alpha,
+                                       const float* __restrict__ D, int ldd, float beta, const float* __restrict__ E,
+                                       int lde, float gamma) {
+  const int64_t total = (int64_t)p.m * p.n;
+  const size_t split_stride = (size_t)p.num_tiles * 128 * p.tn;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / p.n), j = (int)(idx % p.n);
+    const int bm = i / 128, bn = j / p.tn;
+    const int tile = bm * p.num_bn + bn;
+    const size_t off = ((size_t)tile * 128 + (i - bm * 128)) * (size_t)p.tn + (j - bn * p.tn);
+    float s = 0.f;
+    for (int z = 0; z < p.ksplit; ++z) s += p.partial[(size_t)z * split_stride + off];
+    float v = alpha * s;
+    if (D) v += beta * D[(size_t)i * ldd + j];
+    if (E) v += gamma * E[(size_t)i * lde + j];
+    C[(size_t)i * ldc + j] = v;
+  }
+}
+
+inline bool atb_tc_shape_ok(int64_t K, int64_t m, int64_t n) {
+  return m >= 32 && n >= 32 && m % 4 == 0 && n % 4 == 0 && m <= 65536 && n <= 65536 && K >= 1 && K < ((int64_t)1 << 31) - 64;
+}
+inline size_t atb_tc_workspace_bytes(int64_t K, int64_t m, int64_t n) {
+  GramTcParams p;
+  gram_tc_plan(K, n, p, m);
+  return align_up((size_t)p.ksplit * p.num_tiles * 128 * p.tn * sizeof(float));
+}
+
+inline int encode_rowmajor_f32(CUtensorMap* tmap, const float* ptr, int64_t rows, int64_t cols) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)TC_KC};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = get_encode_tiled()(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(TNB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  return TNB_OK;
+}
+
+inline int atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t n, float* C, int ldc, float alpha,
+                      const float* D, int ldd, float beta, const float* E, int lde, float gamma, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  if (!tc_path_available()) return fail(TNB_ERR_UNSUPPORTED, "atb_tc: tcgen05/TMA path needs an sm_100 device");
+  if (!atb_tc_shape_ok(K, m, n)) return fail(TNB_ERR_UNSUPPORTED, "atb_tc: unsupported shape K=%lld m=%lld n=%lld", (long long)K, (long long)m, (long long)n);
+  if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) != 0)
+    return fail(TNB_ERR_INVALID, "atb_tc: operands must be 16-byte aligned");
+  GramTcParams p;
+  gram_tc_plan(K, n, p, m);
+  const size_t need = (size_t)p.ksplit * p.num_tiles * 128 * p.tn * sizeof(float);
+  if (ws_bytes < need) return fail(TNB_ERR_WORKSPACE, "atb_tc: workspace %zu < %zu", ws_bytes, need);
+  p.partial = static_cast<float*>(ws);
+  CUtensorMap ta, tb;
+  TNB_TRY(encode_rowmajor_f32(&ta, A, K, m));
+  TNB_TRY(encode_rowmajor_f32(&tb, B, K, n));
+  static bool attr_set = false;
+  if (!attr_set) {
+    TNB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
+  gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
+  TNB_LAUNCH_CHECK();
+  const int64_t total = m * n;
+  atb_tc_finalize_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(p, C, ldc, alpha, D, ldd,
+                                                                                                 beta, E, lde, gamma);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
 }

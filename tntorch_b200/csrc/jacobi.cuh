@@ -28,28 +28,42 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red /*>=32 
   return out;
 }
 
+template <typename R> struct JacTraits;
+template <> struct JacTraits<double> {
+  static __device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static constexpr double floor_rel = 1e-30;
+};
+template <> struct JacTraits<float> {
+  static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static constexpr float floor_rel = 1e-13f;
+};
+
 // Eigen-decomposition of the symmetric PSD n x n matrix Gin (leading dimension ldg) by ONE-SIDED
-// (Hestenes) Jacobi: W = G V is kept column by column; each warp owns one column pair per round,
+// (Hestenes) Jacobi in precision R (double for the truncation step, float for the b x b problems of the
+// fp32 subspace iteration): W = G V is kept column by column; each warp owns one column pair per round,
 // takes the three inner products with shuffle reductions, rotates its two columns of W and V, and the
 // only block-wide synchronisation is one barrier per round (np-1 rounds per sweep, circle ordering).
-// At convergence the columns of W are orthogonal: W = V diag(lambda), lambda_c = v_c . w_c.
-//   w_out[0..n)   eigenvalues, descending
-//   V_out[n x n]  row-major, column j = eigenvector of w_out[j]
-//   scratch       2*np*np doubles when !SMEM (np = n rounded up to even)
+// The rotation is computed with one sqrt, one division and one rsqrt (the dependent scalar chain is what
+// bounds a round).  At convergence W = V diag(lambda), lambda_c = v_c . w_c.
+//   w_out[0..n)   eigenvalues, descending (fp64)
+//   V_out[n x n]  row-major fp64, column j = eigenvector of w_out[j]
+//   scratch       2*np*np R's when !SMEM (np = n rounded up to even)
 //   info[0]       number of sweeps used (negative if max_sweeps hit without convergence)
-template <bool SMEM>
+template <typename R, bool SMEM>
 __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const double* __restrict__ Gin, int n, int ldg,
                                                                      double* __restrict__ w_out,
                                                                      double* __restrict__ V_out,
-                                                                     double* __restrict__ scratch, int max_sweeps,
-                                                                     double tol, int* __restrict__ info) {
+                                                                     R* __restrict__ scratch, int max_sweeps,
+                                                                     R tol, int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char jac_smem_raw[];
   const int np = n + (n & 1);
   const int m = np >> 1;
-  double* Wt;  // column-major: Wt[c*np + r] = W[r][c]
-  double* Vt;
+  R* Wt;  // column-major: Wt[c*np + r] = W[r][c]
+  R* Vt;
   if (SMEM) {
-    Wt = reinterpret_cast<double*>(jac_smem_raw);
+    Wt = reinterpret_cast<R*>(jac_smem_raw);
     Vt = Wt + (size_t)np * np;
   } else {
     Wt = scratch;
@@ -62,20 +76,32 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
+  // scale so that float never overflows: divide by the largest diagonal entry
+  double dmax_local = 0.0;
+  for (int i = tid; i < n; i += nt) dmax_local = fmax(dmax_local, fabs(Gin[(size_t)i * ldg + i]));
+  for (int o = 16; o > 0; o >>= 1) dmax_local = fmax(dmax_local, __shfl_xor_sync(0xffffffffu, dmax_local, o));
+  if (tid == 0) s_gmax = 0.0;
+  __syncthreads();
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_gmax), (unsigned long long)__double_as_longlong(dmax_local));
+  __syncthreads();
+  const double gscale = s_gmax > 0.0 ? s_gmax : 1.0;  // non-negative doubles order like their bit patterns
+  const double ginv = 1.0 / gscale;
+  __syncthreads();
+
   for (int idx = tid; idx < np * np; idx += nt) {
     const int c = idx / np, r = idx % np;
     double v = 0.0;
-    if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]);  // symmetrise
-    Wt[idx] = v;
-    Vt[idx] = (r == c) ? 1.0 : 0.0;
+    if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]) * ginv;  // symmetrise, scale
+    Wt[idx] = (R)v;
+    Vt[idx] = (r == c) ? (R)1 : (R)0;
   }
   __syncthreads();
-  // scale reference: largest squared column norm (~ lambda_max^2)
+  // reference scale: largest squared column norm (~ lambda_max^2 in scaled units)
   for (int c = warp; c < np; c += nwarps) {
-    double s = 0.0;
-    for (int r = lane; r < np; r += 32) { const double a = Wt[(size_t)c * np + r]; s += a * a; }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_w[c] = s;
+    R sacc = 0;
+    for (int r = lane; r < np; r += 32) { const R a = Wt[(size_t)c * np + r]; sacc += a * a; }
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) s_w[c] = (double)sacc;
   }
   __syncthreads();
   if (tid == 0) {
@@ -84,7 +110,8 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
     s_gmax = g;
   }
   __syncthreads();
-  const double floor2 = 1e-30 * s_gmax;  // pairs of columns both at the noise level are left alone
+  const R floor2 = (R)(JacTraits<R>::floor_rel * s_gmax);  // pairs of columns both at the noise level are left alone
+  const R tol2 = tol * tol;
 
   int sweeps_done = 0;
   bool converged = false;
@@ -103,34 +130,40 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
           q = (step - pi + (np - 1)) % (np - 1);
         }
         if (p > q) { const int t = p; p = q; q = t; }
-        double* wp = Wt + (size_t)p * np;
-        double* wq = Wt + (size_t)q * np;
-        double dpp = 0.0, dqq = 0.0, dpq = 0.0;
+        R* wp = Wt + (size_t)p * np;
+        R* wq = Wt + (size_t)q * np;
+        R dpp = 0, dqq = 0, dpq = 0;
         for (int r = lane; r < np; r += 32) {
-          const double a = wp[r], b = wq[r];
+          const R a = wp[r], b = wq[r];
           dpp = fma(a, a, dpp);
           dqq = fma(b, b, dqq);
           dpq = fma(a, b, dpq);
         }
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           dpp += __shfl_xor_sync(0xffffffffu, dpp, o);
           dqq += __shfl_xor_sync(0xffffffffu, dqq, o);
           dpq += __shfl_xor_sync(0xffffffffu, dpq, o);
         }
-        const double scale = sqrt(dpp * dqq);
-        if (fabs(dpq) > tol * scale && scale > floor2) {  // warp-uniform
+        const R prod = dpp * dqq;
+        if (dpq * dpq > tol2 * prod && prod > floor2 * floor2) {  // warp-uniform
           rot = 1;
-          const double tau = (dqq - dpp) / (2.0 * dpq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          const double c = 1.0 / sqrt(1.0 + t * t);
-          const double s = t * c;
-          double* vp = Vt + (size_t)p * np;
-          double* vq = Vt + (size_t)q * np;
+          // t = sign(tau) / (|tau| + sqrt(1 + tau^2)),  tau = (dqq - dpp) / (2 dpq)
+          //   = sign(h dpq) * 2|dpq| / (|h| + sqrt(h^2 + 4 dpq^2)),  h = dqq - dpp
+          const R h = dqq - dpp;
+          const R twopq = (R)2 * dpq;
+          const R rad = JacTraits<R>::sqrt_(fma(h, h, twopq * twopq));
+          R t = twopq / (fabs(h) + rad);
+          if (h < (R)0) t = -t;
+          const R c = JacTraits<R>::rsqrt_(fma(t, t, (R)1));
+          const R s = t * c;
+          R* vp = Vt + (size_t)p * np;
+          R* vq = Vt + (size_t)q * np;
           for (int r = lane; r < np; r += 32) {
-            const double a = wp[r], b = wq[r];
+            const R a = wp[r], b = wq[r];
             wp[r] = c * a - s * b;
             wq[r] = s * a + c * b;
-            const double x = vp[r], y = vq[r];
+            const R x = vp[r], y = vq[r];
             vp[r] = c * x - s * y;
             vq[r] = s * x + c * y;
           }
@@ -149,12 +182,12 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
     }
   }
 
-  // eigenvalues as Rayleigh quotients lambda_c = v_c . (G v_c) = v_c . w_c ; sort descending; write out
+  // eigenvalues as Rayleigh quotients lambda_c = v_c . (G v_c) = v_c . w_c (fp64 accumulate); sort; write out
   for (int c = warp; c < n; c += nwarps) {
-    double s = 0.0;
-    for (int r = lane; r < np; r += 32) s = fma(Vt[(size_t)c * np + r], Wt[(size_t)c * np + r], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_w[c] = s;
+    double sacc = 0.0;
+    for (int r = lane; r < np; r += 32) sacc = fma((double)Vt[(size_t)c * np + r], (double)Wt[(size_t)c * np + r], sacc);
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) s_w[c] = sacc * gscale;
   }
   __syncthreads();
   for (int i = tid; i < n; i += nt) {
@@ -170,7 +203,7 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += nt) {
     const int k = idx / n, i = idx % n;
-    V_out[(size_t)k * n + s_rank[i]] = Vt[(size_t)i * np + k];
+    V_out[(size_t)k * n + s_rank[i]] = (double)Vt[(size_t)i * np + k];
   }
   if (tid == 0 && info) info[0] = converged ? sweeps_done : -sweeps_done;
 }
@@ -180,24 +213,35 @@ inline size_t jacobi_scratch_doubles(int n) {
   return (size_t)2 * np * np;
 }
 
-// G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles (+ 1 int info at the end).
+// G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles.
+// single_precision: run the rotations in fp32 (for the b x b problems of the fp32 subspace iteration).
 inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, double* scratch, int* info,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool single_precision = false) {
   if (n < 1 || n > JACOBI_MAX_N) return fail(TNB_ERR_UNSUPPORTED, "jacobi_eigh: n=%d outside [1,%d]", n, JACOBI_MAX_N);
   const int np = n + (n & 1);
-  const double tol = 1e-14;  // relative off-diagonal threshold |a_pq| <= tol*sqrt(a_pp*a_qq)
   const int max_sweeps = 30;
-  if (n <= JACOBI_SMEM_MAX_N) {
-    const size_t smem = (size_t)2 * np * np * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N) * (int)sizeof(double)));
-      attr_set = true;
-    }
-    jacobi_eigh_kernel<true><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int maxb = 2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N) * (int)sizeof(double);
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    attr_set = true;
+  }
+  if (single_precision) {
+    const float tol = 2e-6f;  // ~ eps_fp32 * sqrt(n): the accuracy of an fp32 inner product
+    if ((size_t)2 * np * np * sizeof(float) <= (size_t)2 * JACOBI_SMEM_MAX_N * JACOBI_SMEM_MAX_N * sizeof(double))
+      jacobi_eigh_kernel<float, true><<<1, JACOBI_THREADS, (size_t)2 * np * np * sizeof(float), st>>>(
+          G, n, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info);
+    else
+      jacobi_eigh_kernel<float, false><<<1, JACOBI_THREADS, 0, st>>>(G, n, ldg, w, V, reinterpret_cast<float*>(scratch),
+                                                                      max_sweeps, tol, info);
   } else {
-    jacobi_eigh_kernel<false><<<1, JACOBI_THREADS, 0, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    const double tol = 1e-14;  // relative off-diagonal threshold |w_p.w_q| <= tol*|w_p||w_q|
+    if (n <= JACOBI_SMEM_MAX_N)
+      jacobi_eigh_kernel<double, true><<<1, JACOBI_THREADS, (size_t)2 * np * np * sizeof(double), st>>>(
+          G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    else
+      jacobi_eigh_kernel<double, false><<<1, JACOBI_THREADS, 0, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
   }
   TNB_LAUNCH_CHECK();
   return TNB_OK;

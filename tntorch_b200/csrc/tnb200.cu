@@ -239,6 +239,19 @@ int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* wo
   return gram_tc_f32(A, rows, n, G, nullptr, workspace, workspace_bytes, as_stream(stream));
 }
 
+size_t tnb_atb_tc_workspace_bytes(int64_t K, int64_t m, int64_t n) {
+  if (!atb_tc_shape_ok(K, m, n)) return 0;
+  return atb_tc_workspace_bytes(K, m, n) + 256;
+}
+
+int tnb_atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t n, float* C, float alpha,
+                   const float* D, float beta, void* workspace, size_t workspace_bytes, void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !B || !C || !workspace) return fail(TNB_ERR_INVALID, "tnb_atb_tc_f32: null argument");
+  return atb_tc_f32(A, K, m, B, n, C, (int)n, alpha, D, (int)n, beta, nullptr, 0, 0.f, workspace, workspace_bytes,
+                    as_stream(stream));
+}
+
 int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream) {
   TNB_TRY(check_dtype(dtype));
   TNB_TRY(require_device());

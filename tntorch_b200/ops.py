@@ -255,6 +255,25 @@ def gram(A: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
     return G
 
 
+def atb_tensorcore(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, D: Optional[torch.Tensor] = None,
+                   beta: float = 0.0) -> torch.Tensor:
+    """alpha * A^T B + beta * D on the tcgen05 kernel (A: K x m, B: K x n, fp32)."""
+    _require_cuda(A, "atb_tensorcore")
+    A, B = A.contiguous(), B.contiguous()
+    K, m = A.shape
+    n = B.shape[1]
+    L = lib()
+    wsb = L.tnb_atb_tc_workspace_bytes(K, m, n)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, A.device)
+    out = torch.empty(m, n, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(L.tnb_atb_tc_f32(_ptr(A), K, m, _ptr(B), n, _ptr(out), float(alpha), _ptr(D), float(beta), _ptr(ws),
+                               ws.numel(), _stream()))
+    return out
+
+
 def project(A: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
     _require_cuda(A, "project")
     A, V = A.contiguous(), V.contiguous()
