@@ -85,9 +85,33 @@ inline int chfsi_apply(const TB* G, int n, int b, const TB* Yin, const TB* Xin, 
                                          false, (TB*)nullptr, 0, st);
 }
 
-// X <- orthonormal basis of span(X) via two SVQB passes; result left in *Xio, *Xtmp is scratch.
+// X <- orthonormal basis of span(X); result left in *Xio, *Xtmp is scratch.
+//   use_chol = false: two SVQB passes (eigen-decomposition of the scaled Gram matrix; tolerates a
+//                     numerically rank-deficient block — used while the block is still far from converged)
+//   use_chol = true : one Cholesky-QR pass in fp64 (the filtered Ritz vectors are close to orthogonal after
+//                     column scaling; the kernel raises w.jinfo[1] if a pivot says otherwise)
 template <typename TB>
-inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>& w, cudaStream_t st) {
+inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>& w, cudaStream_t st,
+                                bool use_chol = false) {
+  if (use_chol) {
+    GemmPlan pl = plan_gemm(b, b, n, false);
+    TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, *Xio, b, false,
+                                                         reinterpret_cast<double*>(w.partial), w.S, b, 1.0, nullptr, 0,
+                                                         0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
+    const size_t smem = (size_t)2 * b * b * sizeof(double);
+    const bool fits = smem <= (size_t)180 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TNB_CUDA(cudaFuncSetAttribute(chol_orth_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+      attr_set = true;
+    }
+    chol_orth_kernel<TB><<<1, 1024, fits ? smem : 0, st>>>(w.S, b, w.jscratch, w.Tm, w.jinfo + 1, fits ? 1 : 0);
+    TNB_LAUNCH_CHECK();
+    TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,
+                                         nullptr, 0, (TB)0, st)));
+    TB* t = *Xio; *Xio = *Xtmp; *Xtmp = t;
+    return TNB_OK;
+  }
   for (int pass = 0; pass < 2; ++pass) {
     GemmPlan pl = plan_gemm(b, b, n, false);
     TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, *Xio, b, false,
@@ -131,7 +155,7 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
                           double* theta_out, double* X_out, ChfsiStats* stats, cudaStream_t st) {
   if (b < k || b > JACOBI_MAX_N || b > n)
     return fail(TNB_ERR_UNSUPPORTED, "eig_topk: block %d invalid for k=%d n=%d (max %d)", b, k, n, JACOBI_MAX_N);
-  double* h_theta = static_cast<double*>(pinned_scratch((size_t)(b + 2) * sizeof(double)));
+  double* h_theta = static_cast<double*>(pinned_scratch((size_t)(b + 4) * sizeof(double)));
   if (!h_theta) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
   const int max_outer = 40, mmax = 40;
   const double spread = 1e4;
@@ -140,6 +164,9 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
 
   random_fill_kernel<TB><<<grid_for((int64_t)n * b), 256, 0, st>>>(w.X, (int64_t)n * b, 0x1234567u);
   TNB_LAUNCH_CHECK();
+  TNB_CUDA(cudaMemsetAsync(w.jinfo, 0, 4 * sizeof(int), st));
+  int* h_flag = reinterpret_cast<int*>(h_theta + b + 1);
+  bool use_chol = false;  // switched on after the first filtered iteration
   TB* X = w.X;
   TB* Xt = w.Z;  // scratch partner for orthonormalize / RR
   TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st));
@@ -202,12 +229,22 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
     if (stats) stats->products += m + 1;
     X = bufs[icur];
     Xt = bufs[inew];
-    TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st));
+    TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st, use_chol));
     TNB_TRY(chfsi_rayleigh_ritz<TB>(G, n, b, &X, &Xt, w, st));
     TNB_CUDA(cudaMemcpyAsync(h_theta, w.lam, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(cudaMemcpyAsync(h_flag, w.jinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     TNB_CUDA(cudaStreamSynchronize(st));
     double cap = 0.0;
     for (int i = 0; i < k; ++i) cap += h_theta[i];
+    if (h_flag[1] != 0) {
+      // Cholesky saw numerically dependent columns: this iteration's basis is unreliable; go back to the
+      // eigen-decomposition based transform for the rest of the solve and do not test convergence now
+      use_chol = false;
+      TNB_CUDA(cudaMemsetAsync(w.jinfo, 0, 4 * sizeof(int), st));
+      prev = cap < prev ? cap : prev;
+      continue;
+    }
+    use_chol = true;
     if (outer >= 1 && cap - prev <= tol * trace) {
       converged = true;
       ++outer;

@@ -49,6 +49,8 @@ struct GramTcParams {
   uint32_t desc_layout;  // 1 = SWIZZLE_128B_BASE32B (the only MN-major layout tf32 operands accept)
   uint32_t desc_lbo;     // bytes between 32-column groups (one TMA box)
   uint32_t desc_sbo;     // bytes between K atoms (4 rows x 128 B)
+  int fold;              // > 1: the matrix was viewed as (rows/fold) x (fold*n_orig); G = sum of the diagonal blocks
+  int n_orig;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -290,6 +292,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
 // Sum the split-K partial tiles in fp64 (fixed order), mirror to the lower triangle.
 __global__ void gram_tc_finalize_kernel(const GramTcParams p, double* __restrict__ G, float* __restrict__ Gf) {
+  if (p.fold > 1) {  // single 128 x 128 tile; fold the diagonal n_orig x n_orig blocks
+    const int no = p.n_orig;
+    const size_t split_stride = (size_t)p.num_tiles * 128 * p.tn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < no * no; idx += gridDim.x * blockDim.x) {
+      const int i = idx / no, j = idx % no;
+      double s = 0.0;
+      for (int z = 0; z < p.ksplit; ++z)
+        for (int a = 0; a < p.fold; ++a)
+          s += (double)p.partial[(size_t)z * split_stride + (size_t)(a * no + i) * p.tn + (a * no + j)];
+      G[idx] = s;
+      if (Gf) Gf[idx] = (float)s;
+    }
+    return;
+  }
   const int64_t total = (int64_t)p.n * p.n;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -377,11 +393,23 @@ inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p, int64_t m_col
   p.desc_layout = 1;
   p.desc_lbo = TC_BOX_BYTES;
   p.desc_sbo = 512;
+  p.fold = 1;
+  p.n_orig = (int)n;
+}
+
+// Narrow matrices (n = 32 or 64) are viewed as (rows/f) x 128, f = 128/n: one full-width 128 x 128 tile with
+// every TMA box useful (16 KB per stage in flight instead of 8 KB padded with zero boxes); the Gram matrix is
+// the sum of the f diagonal n x n blocks.
+inline int gram_tc_fold(int64_t rows, int64_t n) {
+  if (n >= 128 || n < 32 || 128 % n != 0) return 1;
+  const int f = (int)(128 / n);
+  return (rows % f == 0) ? f : 1;
 }
 
 inline size_t gram_tc_workspace_bytes(int64_t rows, int64_t n) {
   GramTcParams p;
-  gram_tc_plan(rows, n, p);
+  const int f = gram_tc_fold(rows, n);
+  gram_tc_plan(rows / f, n * f, p);
   return align_up((size_t)p.ksplit * p.num_tiles * 128 * p.tn * sizeof(float));
 }
 
@@ -392,7 +420,13 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
   if (!gram_tc_shape_ok(rows, n)) return fail(TNB_ERR_UNSUPPORTED, "gram_tc: unsupported shape rows=%lld n=%lld", (long long)rows, (long long)n);
   if ((reinterpret_cast<uintptr_t>(A) & 15u) != 0) return fail(TNB_ERR_INVALID, "gram_tc: input must be 16-byte aligned");
   GramTcParams p;
+  const int fold = gram_tc_fold(rows, n);
+  const int64_t n_in = n;
+  rows /= fold;
+  n *= fold;
   gram_tc_plan(rows, n, p);
+  p.fold = fold;
+  p.n_orig = (int)n_in;
   const size_t need = (size_t)p.ksplit * p.num_tiles * 128 * p.tn * sizeof(float);
   if (ws_bytes < need) return fail(TNB_ERR_WORKSPACE, "gram_tc: workspace %zu < %zu", ws_bytes, need);
   p.partial = static_cast<float*>(ws);
@@ -416,7 +450,7 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
   dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
   gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, tmap, p);
   TNB_LAUNCH_CHECK();
-  const int64_t total = n * n;
+  const int64_t total = n_in * n_in;
   gram_tc_finalize_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(p, G, Gf);
   TNB_LAUNCH_CHECK();
   return TNB_OK;

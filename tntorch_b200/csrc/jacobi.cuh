@@ -28,30 +28,54 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red /*>=32 
   return out;
 }
 
+// Rotation (c, s) that orthogonalises two columns with squared norms dpp, dqq and inner product dpq:
+//   t = sign(tau)/(|tau| + sqrt(1+tau^2)), tau = (dqq-dpp)/(2 dpq);  c = 1/sqrt(1+t^2);  s = t c.
+// ANY t gives an exactly orthogonal rotation as long as c and s are consistent, so t is evaluated in
+// fp32 on exponent-normalised inputs (MUFU sqrt / division: a handful of instructions instead of three
+// software fp64 divisions/square roots), and only c = rsqrt(1+t^2) is refined to full precision with two
+// Newton steps.  A pair is then annihilated to ~1e-7 relative per rotation instead of 1e-16, which the
+// next sweep finishes (convergence stays superlinear); V stays orthogonal to working precision.
+__device__ __forceinline__ void jacobi_rotation(double dpp, double dqq, double dpq, double& c, double& s) {
+  const double h = dqq - dpp, b2 = 2.0 * dpq;
+  const double big = fmax(fabs(h), fabs(b2));
+  const int e = ilogb(big);
+  const float hf = (float)scalbn(h, -e), bf = (float)scalbn(b2, -e);
+  const float radf = sqrtf(fmaf(hf, hf, bf * bf));
+  float tf = __fdividef(bf, fabsf(hf) + radf);
+  if (hf < 0.f) tf = -tf;
+  const double t = (double)tf;
+  const double x = fma(t, t, 1.0);  // in [1, 2]
+  double y = (double)rsqrtf((float)x);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  c = y;
+  s = t * y;
+}
+__device__ __forceinline__ void jacobi_rotation(float dpp, float dqq, float dpq, float& c, float& s) {
+  const float h = dqq - dpp, b2 = 2.f * dpq;
+  const float radf = sqrtf(fmaf(h, h, b2 * b2));
+  float t = __fdividef(b2, fabsf(h) + radf);
+  if (h < 0.f) t = -t;
+  c = rsqrtf(fmaf(t, t, 1.f));
+  s = t * c;
+}
+
 template <typename R> struct JacTraits;
-template <> struct JacTraits<double> {
-  static __device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
-  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-  static constexpr double floor_rel = 1e-30;
-};
-template <> struct JacTraits<float> {
-  static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
-  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-  static constexpr float floor_rel = 1e-13f;
-};
+template <> struct JacTraits<double> { static constexpr double floor_rel = 1e-30; };
+template <> struct JacTraits<float> { static constexpr float floor_rel = 1e-13f; };
 
 // Eigen-decomposition of the symmetric PSD n x n matrix Gin (leading dimension ldg) by ONE-SIDED
 // (Hestenes) Jacobi in precision R (double for the truncation step, float for the b x b problems of the
-// fp32 subspace iteration): W = G V is kept column by column; each warp owns one column pair per round,
-// takes the three inner products with shuffle reductions, rotates its two columns of W and V, and the
-// only block-wide synchronisation is one barrier per round (np-1 rounds per sweep, circle ordering).
-// The rotation is computed with one sqrt, one division and one rsqrt (the dependent scalar chain is what
-// bounds a round).  At convergence W = V diag(lambda), lambda_c = v_c . w_c.
+// fp32 subspace iteration).  W = G V is kept column by column; a group of LANES lanes owns one column
+// pair per round (32/LANES pairs per warp, so the per-pair scalar work is issued once per warp), takes
+// the three inner products with shuffle reductions, rotates its two columns of W and V; the only
+// block-wide synchronisation is one barrier per round (np-1 rounds per sweep, circle ordering).
+// At convergence W = V diag(lambda), lambda_c = v_c . w_c.
 //   w_out[0..n)   eigenvalues, descending (fp64)
 //   V_out[n x n]  row-major fp64, column j = eigenvector of w_out[j]
 //   scratch       2*np*np R's when !SMEM (np = n rounded up to even)
 //   info[0]       number of sweeps used (negative if max_sweeps hit without convergence)
-template <typename R, bool SMEM>
+template <typename R, bool SMEM, int LANES>
 __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const double* __restrict__ Gin, int n, int ldg,
                                                                      double* __restrict__ w_out,
                                                                      double* __restrict__ V_out,
@@ -60,14 +84,15 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   extern __shared__ __align__(16) unsigned char jac_smem_raw[];
   const int np = n + (n & 1);
   const int m = np >> 1;
-  R* Wt;  // column-major: Wt[c*np + r] = W[r][c]
+  const int ld = np + 8;  // padded column stride: the lane groups of a warp hit different banks
+  R* Wt;  // column-major: Wt[c*ld + r] = W[r][c]
   R* Vt;
   if (SMEM) {
     Wt = reinterpret_cast<R*>(jac_smem_raw);
-    Vt = Wt + (size_t)np * np;
+    Vt = Wt + (size_t)np * ld;
   } else {
     Wt = scratch;
-    Vt = scratch + (size_t)np * np;
+    Vt = scratch + (size_t)np * ld;
   }
   __shared__ double s_w[JACOBI_MAX_N + 2];
   __shared__ int s_rank[JACOBI_MAX_N + 2];
@@ -75,16 +100,19 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   __shared__ int s_nrot;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  constexpr int PPW = 32 / LANES;           // pairs per warp per pass
+  const int sub = lane / LANES, sl = lane % LANES;
 
-  // scale so that float never overflows: divide by the largest diagonal entry
+  // scale by the largest diagonal entry (keeps fp32 in range; eigenvalues are scaled back at the end)
   double dmax_local = 0.0;
   for (int i = tid; i < n; i += nt) dmax_local = fmax(dmax_local, fabs(Gin[(size_t)i * ldg + i]));
   for (int o = 16; o > 0; o >>= 1) dmax_local = fmax(dmax_local, __shfl_xor_sync(0xffffffffu, dmax_local, o));
   if (tid == 0) s_gmax = 0.0;
   __syncthreads();
-  if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_gmax), (unsigned long long)__double_as_longlong(dmax_local));
+  if (lane == 0)  // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(&s_gmax), (unsigned long long)__double_as_longlong(dmax_local));
   __syncthreads();
-  const double gscale = s_gmax > 0.0 ? s_gmax : 1.0;  // non-negative doubles order like their bit patterns
+  const double gscale = s_gmax > 0.0 ? s_gmax : 1.0;
   const double ginv = 1.0 / gscale;
   __syncthreads();
 
@@ -92,14 +120,14 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
     const int c = idx / np, r = idx % np;
     double v = 0.0;
     if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]) * ginv;  // symmetrise, scale
-    Wt[idx] = (R)v;
-    Vt[idx] = (r == c) ? (R)1 : (R)0;
+    Wt[(size_t)c * ld + r] = (R)v;
+    Vt[(size_t)c * ld + r] = (r == c) ? (R)1 : (R)0;
   }
   __syncthreads();
   // reference scale: largest squared column norm (~ lambda_max^2 in scaled units)
   for (int c = warp; c < np; c += nwarps) {
     R sacc = 0;
-    for (int r = lane; r < np; r += 32) { const R a = Wt[(size_t)c * np + r]; sacc += a * a; }
+    for (int r = lane; r < np; r += 32) { const R a = Wt[(size_t)c * ld + r]; sacc += a * a; }
     for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
     if (lane == 0) s_w[c] = (double)sacc;
   }
@@ -120,46 +148,45 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
     __syncthreads();
     int rot = 0;
     for (int step = 0; step < np - 1; ++step) {
-      for (int pi = warp; pi < m; pi += nwarps) {
-        int p, q;
-        if (pi == 0) {
-          p = np - 1;
-          q = step % (np - 1);
-        } else {
-          p = (step + pi) % (np - 1);
-          q = (step - pi + (np - 1)) % (np - 1);
+      for (int base = warp * PPW; base < m; base += nwarps * PPW) {  // warp-uniform trip count
+        const int pi = base + sub;
+        const bool active = pi < m;
+        int p = 0, q = 1;
+        if (active) {
+          if (pi == 0) {
+            p = np - 1;
+            q = step % (np - 1);
+          } else {
+            p = (step + pi) % (np - 1);
+            q = (step - pi + (np - 1)) % (np - 1);
+          }
+          if (p > q) { const int t = p; p = q; q = t; }
         }
-        if (p > q) { const int t = p; p = q; q = t; }
-        R* wp = Wt + (size_t)p * np;
-        R* wq = Wt + (size_t)q * np;
+        R* wp = Wt + (size_t)p * ld;
+        R* wq = Wt + (size_t)q * ld;
         R dpp = 0, dqq = 0, dpq = 0;
-        for (int r = lane; r < np; r += 32) {
-          const R a = wp[r], b = wq[r];
-          dpp = fma(a, a, dpp);
-          dqq = fma(b, b, dqq);
-          dpq = fma(a, b, dpq);
+        if (active) {
+          for (int r = sl; r < np; r += LANES) {
+            const R a = wp[r], b = wq[r];
+            dpp = fma(a, a, dpp);
+            dqq = fma(b, b, dqq);
+            dpq = fma(a, b, dpq);
+          }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = LANES / 2; o > 0; o >>= 1) {
           dpp += __shfl_xor_sync(0xffffffffu, dpp, o);
           dqq += __shfl_xor_sync(0xffffffffu, dqq, o);
           dpq += __shfl_xor_sync(0xffffffffu, dpq, o);
         }
         const R prod = dpp * dqq;
-        if (dpq * dpq > tol2 * prod && prod > floor2 * floor2) {  // warp-uniform
+        if (active && dpq * dpq > tol2 * prod && prod > floor2 * floor2) {  // uniform within the lane group
           rot = 1;
-          // t = sign(tau) / (|tau| + sqrt(1 + tau^2)),  tau = (dqq - dpp) / (2 dpq)
-          //   = sign(h dpq) * 2|dpq| / (|h| + sqrt(h^2 + 4 dpq^2)),  h = dqq - dpp
-          const R h = dqq - dpp;
-          const R twopq = (R)2 * dpq;
-          const R rad = JacTraits<R>::sqrt_(fma(h, h, twopq * twopq));
-          R t = twopq / (fabs(h) + rad);
-          if (h < (R)0) t = -t;
-          const R c = JacTraits<R>::rsqrt_(fma(t, t, (R)1));
-          const R s = t * c;
-          R* vp = Vt + (size_t)p * np;
-          R* vq = Vt + (size_t)q * np;
-          for (int r = lane; r < np; r += 32) {
+          R c, s;
+          jacobi_rotation(dpp, dqq, dpq, c, s);
+          R* vp = Vt + (size_t)p * ld;
+          R* vq = Vt + (size_t)q * ld;
+          for (int r = sl; r < np; r += LANES) {
             const R a = wp[r], b = wq[r];
             wp[r] = c * a - s * b;
             wq[r] = s * a + c * b;
@@ -171,7 +198,7 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
       }
       __syncthreads();
     }
-    if (lane == 0 && rot) atomicAdd(&s_nrot, 1);
+    if (rot) atomicAdd(&s_nrot, 1);
     __syncthreads();
     sweeps_done = sweep + 1;
     const int nrot = s_nrot;
@@ -185,7 +212,7 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   // eigenvalues as Rayleigh quotients lambda_c = v_c . (G v_c) = v_c . w_c (fp64 accumulate); sort; write out
   for (int c = warp; c < n; c += nwarps) {
     double sacc = 0.0;
-    for (int r = lane; r < np; r += 32) sacc = fma((double)Vt[(size_t)c * np + r], (double)Wt[(size_t)c * np + r], sacc);
+    for (int r = lane; r < np; r += 32) sacc = fma((double)Vt[(size_t)c * ld + r], (double)Wt[(size_t)c * ld + r], sacc);
     for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
     if (lane == 0) s_w[c] = sacc * gscale;
   }
@@ -203,14 +230,24 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += nt) {
     const int k = idx / n, i = idx % n;
-    V_out[(size_t)k * n + s_rank[i]] = (double)Vt[(size_t)i * np + k];
+    V_out[(size_t)k * n + s_rank[i]] = (double)Vt[(size_t)i * ld + k];
   }
   if (tid == 0 && info) info[0] = converged ? sweeps_done : -sweeps_done;
 }
 
 inline size_t jacobi_scratch_doubles(int n) {
   const int np = n + (n & 1);
-  return (size_t)2 * np * np;
+  return (size_t)2 * np * (np + 8);
+}
+
+template <typename R, bool SMEM>
+inline void jacobi_launch(int n, size_t smem, const double* G, int ldg, double* w, double* V, R* scratch, int max_sweeps,
+                          R tol, int* info, cudaStream_t st) {
+  // lanes per column pair: small problems use 8 (4 pairs per warp) so that the per-pair scalar work is shared
+  if (n <= 128)
+    jacobi_eigh_kernel<R, SMEM, 8><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+  else
+    jacobi_eigh_kernel<R, SMEM, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
 }
 
 // G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles.
@@ -221,27 +258,28 @@ inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, do
   const int np = n + (n & 1);
   const int max_sweeps = 30;
   static bool attr_set = false;
+  const int maxb = 2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N + 8) * (int)sizeof(double);
   if (!attr_set) {
-    const int maxb = 2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N) * (int)sizeof(double);
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
     attr_set = true;
   }
   if (single_precision) {
     const float tol = 2e-6f;  // ~ eps_fp32 * sqrt(n): the accuracy of an fp32 inner product
-    if ((size_t)2 * np * np * sizeof(float) <= (size_t)2 * JACOBI_SMEM_MAX_N * JACOBI_SMEM_MAX_N * sizeof(double))
-      jacobi_eigh_kernel<float, true><<<1, JACOBI_THREADS, (size_t)2 * np * np * sizeof(float), st>>>(
-          G, n, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info);
+    const size_t smem = (size_t)2 * np * (np + 8) * sizeof(float);
+    if (smem <= (size_t)maxb)
+      jacobi_launch<float, true>(n, smem, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
     else
-      jacobi_eigh_kernel<float, false><<<1, JACOBI_THREADS, 0, st>>>(G, n, ldg, w, V, reinterpret_cast<float*>(scratch),
-                                                                      max_sweeps, tol, info);
+      jacobi_launch<float, false>(n, 0, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
   } else {
-    const double tol = 1e-14;  // relative off-diagonal threshold |w_p.w_q| <= tol*|w_p||w_q|
-    if (n <= JACOBI_SMEM_MAX_N)
-      jacobi_eigh_kernel<double, true><<<1, JACOBI_THREADS, (size_t)2 * np * np * sizeof(double), st>>>(
-          G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    const double tol = 1e-14;  // relative threshold |w_p.w_q| <= tol*|w_p||w_q|
+    const size_t smem = (size_t)2 * np * (np + 8) * sizeof(double);
+    if (smem <= (size_t)maxb)
+      jacobi_launch<double, true>(n, smem, G, ldg, w, V, scratch, max_sweeps, tol, info, st);
     else
-      jacobi_eigh_kernel<double, false><<<1, JACOBI_THREADS, 0, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+      jacobi_launch<double, false>(n, 0, G, ldg, w, V, scratch, max_sweeps, tol, info, st);
   }
   TNB_LAUNCH_CHECK();
   return TNB_OK;

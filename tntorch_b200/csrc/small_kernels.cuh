@@ -161,6 +161,66 @@ __global__ void svqb_finish_kernel(const double* __restrict__ Q, const double* _
   }
 }
 
+// Cholesky-QR transform for a block whose (column-scaled) Gram matrix S is safely positive definite:
+//   d_i = 1/sqrt(S_ii),  D S D = L L^T,  T = D L^{-T}   =>   (Y T)^T (Y T) = I.
+// One CTA, fp64; b <= 256.  scratch holds L and L^{-1} (2*b*b doubles) when they do not fit shared memory.
+// A pivot below 1e-11 (numerically dependent columns) raises *flag and is clamped: the caller then
+// falls back to the eigen-decomposition based SVQB transform.
+template <typename TB>
+__global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restrict__ S, int b, double* scratch,
+                                                         TB* __restrict__ T, int* flag, int use_smem) {
+  extern __shared__ __align__(16) unsigned char chol_smem_raw[];
+  __shared__ double s_d[JACOBI_MAX_N];
+  double* L = use_smem ? reinterpret_cast<double*>(chol_smem_raw) : scratch;
+  double* Li = L + (size_t)b * b;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < b; i += nt) {
+    const double v = S[(size_t)i * b + i];
+    s_d[i] = v > 1e-300 ? rsqrt(v) : 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < b * b; idx += nt) {
+    const int i = idx / b, j = idx % b;
+    L[idx] = (j <= i) ? S[idx] * s_d[i] * s_d[j] : 0.0;
+    Li[idx] = 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < b; ++k) {
+    if (tid == 0) {
+      double piv = L[(size_t)k * b + k];
+      if (!(piv > 1e-11)) {
+        *flag = 1;
+        piv = 1e-11;
+      }
+      L[(size_t)k * b + k] = sqrt(piv);
+    }
+    __syncthreads();
+    const double inv = 1.0 / L[(size_t)k * b + k];
+    for (int i = k + 1 + tid; i < b; i += nt) L[(size_t)i * b + k] *= inv;
+    __syncthreads();
+    const int rem = b - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+      if (j <= i) L[(size_t)i * b + j] -= L[(size_t)i * b + k] * L[(size_t)j * b + k];
+    }
+    __syncthreads();
+  }
+  // L^{-1}, one thread per column
+  for (int j = tid; j < b; j += nt) {
+    Li[(size_t)j * b + j] = 1.0 / L[(size_t)j * b + j];
+    for (int i = j + 1; i < b; ++i) {
+      double acc = 0.0;
+      for (int k = j; k < i; ++k) acc = fma(L[(size_t)i * b + k], Li[(size_t)k * b + j], acc);
+      Li[(size_t)i * b + j] = -acc / L[(size_t)i * b + i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < b * b; idx += nt) {
+    const int i = idx / b, j = idx % b;
+    T[idx] = (TB)((j >= i) ? s_d[i] * Li[(size_t)j * b + i] : 0.0);
+  }
+}
+
 inline int grid_for(int64_t n, int block = 256, int cap = 4096) {
   int64_t g = ceil_div<int64_t>(n, block);
   if (g < 1) g = 1;
