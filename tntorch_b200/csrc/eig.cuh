@@ -166,10 +166,10 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
   TNB_LAUNCH_CHECK();
   TNB_CUDA(cudaMemsetAsync(w.jinfo, 0, 4 * sizeof(int), st));
   int* h_flag = reinterpret_cast<int*>(h_theta + b + 1);
-  bool use_chol = false;  // switched on after the first filtered iteration
+  bool use_chol = true;   // Cholesky-QR; the eigen-decomposition based SVQB only after a flagged breakdown
   TB* X = w.X;
   TB* Xt = w.Z;  // scratch partner for orthonormalize / RR
-  TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st));
+  TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st, true));  // a random block is well conditioned
   TNB_TRY(chfsi_rayleigh_ritz<TB>(G, n, b, &X, &Xt, w, st));
   if (stats) stats->products += 1;
   TNB_CUDA(cudaMemcpyAsync(h_theta, w.lam, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -244,7 +244,6 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
       prev = cap < prev ? cap : prev;
       continue;
     }
-    use_chol = true;
     if (outer >= 1 && cap - prev <= tol * trace) {
       converged = true;
       ++outer;

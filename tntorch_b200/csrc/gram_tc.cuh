@@ -312,13 +312,10 @@ __global__ void gram_tc_finalize_kernel(const GramTcParams p, double* __restrict
     const int i = (int)(idx / p.n), j = (int)(idx % p.n);
     const int ii = i <= j ? i : j, jj = i <= j ? j : i;
     const int bm = ii / 128, bn = jj / p.tn;
-    // flat index of (bm, bn) among kept tiles
+    // flat index of (bm, bn) among kept tiles: row a keeps the column tiles b >= first(a) = floor(a*128 / tn)
     int tile = 0;
-    for (int a = 0; a < p.num_bm; ++a)
-      for (int b = 0; b < p.num_bn; ++b)
-        if ((b + 1) * p.tn > a * 128) {
-          if (a < bm || (a == bm && b < bn)) ++tile;
-        }
+    for (int a = 0; a < bm; ++a) tile += p.num_bn - (a * 128) / p.tn;
+    tile += bn - (bm * 128) / p.tn;
     const size_t off = ((size_t)tile * 128 + (ii - bm * 128)) * (size_t)p.tn + (jj - bn * p.tn);
     const size_t split_stride = (size_t)p.num_tiles * 128 * p.tn;
     double s = 0.0;

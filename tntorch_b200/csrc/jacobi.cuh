@@ -38,8 +38,12 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red /*>=32 
 __device__ __forceinline__ void jacobi_rotation(double dpp, double dqq, double dpq, double& c, double& s) {
   const double h = dqq - dpp, b2 = 2.0 * dpq;
   const double big = fmax(fabs(h), fabs(b2));
-  const int e = ilogb(big);
-  const float hf = (float)scalbn(h, -e), bf = (float)scalbn(b2, -e);
+  // 2^-e with e = exponent of big, built from the exponent bits (big is a normal number: dpq passed the threshold)
+  const int ebits = (__double2hiint(big) >> 20) & 0x7ff;
+  int sbits = 2046 - ebits;               // biased exponent of 2^-(e)
+  sbits = sbits < 1 ? 1 : (sbits > 2046 ? 2046 : sbits);
+  const double scale = __hiloint2double(sbits << 20, 0);
+  const float hf = (float)(h * scale), bf = (float)(b2 * scale);
   const float radf = sqrtf(fmaf(hf, hf, bf * bf));
   float tf = __fdividef(bf, fabsf(hf) + radf);
   if (hf < 0.f) tf = -tf;
@@ -75,7 +79,7 @@ template <> struct JacTraits<float> { static constexpr float floor_rel = 1e-13f;
 //   V_out[n x n]  row-major fp64, column j = eigenvector of w_out[j]
 //   scratch       2*np*np R's when !SMEM (np = n rounded up to even)
 //   info[0]       number of sweeps used (negative if max_sweeps hit without convergence)
-template <typename R, bool SMEM, int LANES>
+template <typename R, bool SMEM, int LANES, int EPL>
 __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const double* __restrict__ Gin, int n, int ldg,
                                                                      double* __restrict__ w_out,
                                                                      double* __restrict__ V_out,
@@ -155,23 +159,32 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
         if (active) {
           if (pi == 0) {
             p = np - 1;
-            q = step % (np - 1);
-          } else {
-            p = (step + pi) % (np - 1);
-            q = (step - pi + (np - 1)) % (np - 1);
+            q = step;  // step < np - 1
+          } else {      // circle method: (step + pi) and (step - pi) modulo np - 1
+            p = step + pi;
+            if (p >= np - 1) p -= np - 1;
+            q = step - pi;
+            if (q < 0) q += np - 1;
           }
           if (p > q) { const int t = p; p = q; q = t; }
         }
         R* wp = Wt + (size_t)p * ld;
         R* wq = Wt + (size_t)q * ld;
+        // this lane's slice of both columns lives in registers for the whole pair update
+        R a[EPL], bq[EPL];
         R dpp = 0, dqq = 0, dpq = 0;
-        if (active) {
-          for (int r = sl; r < np; r += LANES) {
-            const R a = wp[r], b = wq[r];
-            dpp = fma(a, a, dpp);
-            dqq = fma(b, b, dqq);
-            dpq = fma(a, b, dpq);
-          }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          const int r = sl + i * LANES;
+          const bool ok = active && r < np;
+          a[i] = ok ? wp[r] : (R)0;
+          bq[i] = ok ? wq[r] : (R)0;
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          dpp = fma(a[i], a[i], dpp);
+          dqq = fma(bq[i], bq[i], dqq);
+          dpq = fma(a[i], bq[i], dpq);
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) {
@@ -186,13 +199,16 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
           jacobi_rotation(dpp, dqq, dpq, c, s);
           R* vp = Vt + (size_t)p * ld;
           R* vq = Vt + (size_t)q * ld;
-          for (int r = sl; r < np; r += LANES) {
-            const R a = wp[r], b = wq[r];
-            wp[r] = c * a - s * b;
-            wq[r] = s * a + c * b;
-            const R x = vp[r], y = vq[r];
-            vp[r] = c * x - s * y;
-            vq[r] = s * x + c * y;
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) {
+            const int r = sl + i * LANES;
+            if (r < np) {
+              const R x = vp[r], y = vq[r];
+              wp[r] = c * a[i] - s * bq[i];
+              wq[r] = s * a[i] + c * bq[i];
+              vp[r] = c * x - s * y;
+              vq[r] = s * x + c * y;
+            }
           }
         }
       }
@@ -243,11 +259,13 @@ inline size_t jacobi_scratch_doubles(int n) {
 template <typename R, bool SMEM>
 inline void jacobi_launch(int n, size_t smem, const double* G, int ldg, double* w, double* V, R* scratch, int max_sweeps,
                           R tol, int* info, cudaStream_t st) {
-  // lanes per column pair: small problems use 8 (4 pairs per warp) so that the per-pair scalar work is shared
-  if (n <= 128)
-    jacobi_eigh_kernel<R, SMEM, 8><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+  // lanes per column pair (LANES) x elements per lane (EPL) >= n; small problems use 8 lanes (4 pairs per warp)
+  if (n <= 64)
+    jacobi_eigh_kernel<R, SMEM, 8, 8><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+  else if (n <= 128)
+    jacobi_eigh_kernel<R, SMEM, 8, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
   else
-    jacobi_eigh_kernel<R, SMEM, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 16, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
 }
 
 // G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles.
@@ -260,10 +278,12 @@ inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, do
   static bool attr_set = false;
   const int maxb = 2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N + 8) * (int)sizeof(double);
   if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
     attr_set = true;
   }
   if (single_precision) {

@@ -205,13 +205,19 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
     }
     __syncthreads();
   }
-  // L^{-1}, one thread per column
-  for (int j = tid; j < b; j += nt) {
-    Li[(size_t)j * b + j] = 1.0 / L[(size_t)j * b + j];
-    for (int i = j + 1; i < b; ++i) {
-      double acc = 0.0;
-      for (int k = j; k < i; ++k) acc = fma(L[(size_t)i * b + k], Li[(size_t)k * b + j], acc);
-      Li[(size_t)i * b + j] = -acc / L[(size_t)i * b + i];
+  // L^{-1}: one warp per column j (forward substitution, the inner sum split over the lanes)
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int j = warp; j < b; j += nwarps) {
+      if (lane == 0) Li[(size_t)j * b + j] = 1.0 / L[(size_t)j * b + j];
+      __syncwarp();
+      for (int i = j + 1; i < b; ++i) {
+        double acc = 0.0;
+        for (int k = j + lane; k < i; k += 32) acc = fma(L[(size_t)i * b + k], Li[(size_t)k * b + j], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) Li[(size_t)i * b + j] = -acc / L[(size_t)i * b + i];
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
