@@ -22,18 +22,19 @@ __global__ void __launch_bounds__(256) project_f32_kernel(const float* __restric
   __shared__ __align__(16) float Vs[2][KC][RP];
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
-  const int64_t row0 = (int64_t)blockIdx.x * BR;
   float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float4 areg[A4];
   float vreg[VN];
   const int nchunks = (n + KC - 1) / KC;
+  const int64_t nblocks = (rows + BR - 1) / BR;
+  // persistent CTA: a flat stream of (row block, k chunk) work items, software-pipelined through registers
+  // across row-block boundaries so that global loads are always one chunk ahead of the FFMAs
+  const int64_t my_blocks = (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t total = my_blocks * nchunks;
 
-  auto prefetch = [&](int c) {
-    const int k0 = c * KC;
+  auto prefetch = [&](int64_t item) {
+    const int64_t row0 = (blockIdx.x + (item / nchunks) * (int64_t)gridDim.x) * BR;
+    const int k0 = (int)(item % nchunks) * KC;
 #pragma unroll
     for (int i = 0; i < A4; ++i) {
       const int idx = tid + i * 256;
@@ -70,12 +71,19 @@ __global__ void __launch_bounds__(256) project_f32_kernel(const float* __restric
     }
   };
 
-  prefetch(0);
-  for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
+  if (total > 0) prefetch(0);
+  for (int64_t item = 0; item < total; ++item) {
+    const int buf = (int)(item & 1);
+    const int c = (int)(item % nchunks);
+    if (c == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
     stage(buf);
     __syncthreads();
-    if (c + 1 < nchunks) prefetch(c + 1);
+    if (item + 1 < total) prefetch(item + 1);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
@@ -87,18 +95,21 @@ __global__ void __launch_bounds__(256) project_f32_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-  }
+    if (c == nchunks - 1) {
+      const int64_t row0 = (blockIdx.x + (item / nchunks) * (int64_t)gridDim.x) * BR;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t grow = row0 + ty * 4 + i;
-    if (grow >= rows) continue;
-    float* out = C + grow * r + tx * 4;
-    if ((r & 3) == 0 && tx * 4 + 3 < r) {
-      *reinterpret_cast<float4*>(out) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    } else {
+      for (int i = 0; i < 4; ++i) {
+        const int64_t grow = row0 + ty * 4 + i;
+        if (grow >= rows) continue;
+        float* out = C + grow * r + tx * 4;
+        if ((r & 3) == 0 && tx * 4 + 3 < r) {
+          __stcs(reinterpret_cast<float4*>(out), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (tx * 4 + j < r) out[j] = acc[i][j];
+          for (int j = 0; j < 4; ++j)
+            if (tx * 4 + j < r) out[j] = acc[i][j];
+        }
+      }
     }
   }
 }
@@ -111,8 +122,9 @@ inline bool project_f32_fast_ok(int64_t rows, int64_t n, int64_t r, const void* 
 inline int project_f32_fast(const float* A, int64_t rows, int64_t n, const float* V, int r, float* C, cudaStream_t st) {
   const int tx = r <= 32 ? 8 : 16;  // 128 x 32 or 64 x 64 output tile (static shared memory stays below 48 KB)
   const int br = (256 / tx) * 4;
-  const int64_t blocks = ceil_div<int64_t>(rows, br);
-  if (blocks > 2147483647LL) return fail(TNB_ERR_UNSUPPORTED, "project: too many row blocks");
+  int64_t blocks = ceil_div<int64_t>(rows, br);
+  const int sms = device_info().valid ? device_info().sm_count : 148;
+  if (blocks > (int64_t)sms * 3) blocks = (int64_t)sms * 3;  // persistent: 3 resident CTAs per SM loop over the row blocks
   if (tx == 8)
     project_f32_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(A, rows, (int)n, V, r, C);
   else
