@@ -260,10 +260,11 @@ template <typename R, bool SMEM>
 inline void jacobi_launch(int n, size_t smem, const double* G, int ldg, double* w, double* V, R* scratch, int max_sweeps,
                           R tol, int* info, cudaStream_t st) {
   // lanes per column pair (LANES) x elements per lane (EPL) >= n; small problems use 8 lanes (4 pairs per warp)
+  // the block is sized to the warps that own a pair (idle warps would only lengthen every barrier)
   if (n <= 64)
-    jacobi_eigh_kernel<R, SMEM, 8, 8><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 8, 8><<<1, 256, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
   else if (n <= 128)
-    jacobi_eigh_kernel<R, SMEM, 8, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 8, 16><<<1, 512, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
   else
     jacobi_eigh_kernel<R, SMEM, 16, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
 }

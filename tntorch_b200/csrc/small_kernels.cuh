@@ -185,26 +185,30 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
     Li[idx] = 0.0;
   }
   __syncthreads();
+  // right-looking Cholesky with ONE barrier per column: the trailing update uses the unscaled column k and
+  // 1/pivot; column k is final after step k, so its scaling by 1/sqrt(pivot) is deferred to a single pass.
+  __shared__ double s_piv[JACOBI_MAX_N];
   for (int k = 0; k < b; ++k) {
-    if (tid == 0) {
-      double piv = L[(size_t)k * b + k];
-      if (!(piv > 1e-11)) {
-        *flag = 1;
-        piv = 1e-11;
-      }
-      L[(size_t)k * b + k] = sqrt(piv);
+    double piv = L[(size_t)k * b + k];  // broadcast read
+    if (!(piv > 1e-11)) {
+      if (tid == 0) *flag = 1;
+      piv = 1e-11;
     }
-    __syncthreads();
-    const double inv = 1.0 / L[(size_t)k * b + k];
-    for (int i = k + 1 + tid; i < b; i += nt) L[(size_t)i * b + k] *= inv;
-    __syncthreads();
+    if (tid == 0) s_piv[k] = piv;
+    const double ipiv = 1.0 / piv;
     const int rem = b - k - 1;
     for (int idx = tid; idx < rem * rem; idx += nt) {
       const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
-      if (j <= i) L[(size_t)i * b + j] -= L[(size_t)i * b + k] * L[(size_t)j * b + k];
+      if (j <= i) L[(size_t)i * b + j] -= L[(size_t)i * b + k] * L[(size_t)j * b + k] * ipiv;
     }
     __syncthreads();
   }
+  for (int idx = tid; idx < b * b; idx += nt) {
+    const int i = idx / b, k = idx % b;
+    if (k < i) L[idx] *= rsqrt(s_piv[k]);
+    else if (k == i) L[idx] = sqrt(s_piv[k]);
+  }
+  __syncthreads();
   // L^{-1}: one warp per column j (forward substitution, the inner sum split over the lanes)
   {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
