@@ -138,7 +138,7 @@ inline int chfsi_rayleigh_ritz(const TB* G, int n, int b, TB** Xio, TB** Xtmp, C
   TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, w.W, b, false,
                                                        reinterpret_cast<double*>(w.partial), w.S, b, 1.0, nullptr, 0,
                                                        0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
-  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value));
+  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value, 2e-5));
   convert_kernel<double, TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.Tm, (int64_t)b * b);
   TNB_LAUNCH_CHECK();
   TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,

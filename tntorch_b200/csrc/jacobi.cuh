@@ -271,8 +271,10 @@ inline void jacobi_launch(int n, size_t smem, const double* G, int ldg, double* 
 
 // G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles.
 // single_precision: run the rotations in fp32 (for the b x b problems of the fp32 subspace iteration).
+// loose_tol > 0 overrides the convergence threshold (Rayleigh-Ritz inside the subspace iteration only needs the
+// Ritz basis to ~1e-5: the rotations stay exactly orthogonal and the captured energy is second order in it).
 inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, double* scratch, int* info,
-                       cudaStream_t st, bool single_precision = false) {
+                       cudaStream_t st, bool single_precision = false, double loose_tol = 0.0) {
   if (n < 1 || n > JACOBI_MAX_N) return fail(TNB_ERR_UNSUPPORTED, "jacobi_eigh: n=%d outside [1,%d]", n, JACOBI_MAX_N);
   const int np = n + (n & 1);
   const int max_sweeps = 30;
@@ -288,14 +290,14 @@ inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, do
     attr_set = true;
   }
   if (single_precision) {
-    const float tol = 2e-6f;  // ~ eps_fp32 * sqrt(n): the accuracy of an fp32 inner product
+    const float tol = loose_tol > 0.0 ? (float)loose_tol : 2e-6f;  // default ~ eps_fp32 * sqrt(n)
     const size_t smem = (size_t)2 * np * (np + 8) * sizeof(float);
     if (smem <= (size_t)maxb)
       jacobi_launch<float, true>(n, smem, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
     else
       jacobi_launch<float, false>(n, 0, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
   } else {
-    const double tol = 1e-14;  // relative threshold |w_p.w_q| <= tol*|w_p||w_q|
+    const double tol = loose_tol > 0.0 ? loose_tol : 1e-14;  // relative threshold |w_p.w_q| <= tol*|w_p||w_q|
     const size_t smem = (size_t)2 * np * (np + 8) * sizeof(double);
     if (smem <= (size_t)maxb)
       jacobi_launch<double, true>(n, smem, G, ldg, w, V, scratch, max_sweeps, tol, info, st);

@@ -59,10 +59,13 @@ __global__ void __launch_bounds__(256) project_f32_kernel(const float* __restric
     for (int i = 0; i < A4; ++i) {
       const int idx = tid + i * 256;
       const int lrow = idx >> 3, kg = idx & 7;
-      As[buf][kg * 4 + 0][lrow] = areg[i].x;
-      As[buf][kg * 4 + 1][lrow] = areg[i].y;
-      As[buf][kg * 4 + 2][lrow] = areg[i].z;
-      As[buf][kg * 4 + 3][lrow] = areg[i].w;
+      // XOR-swizzle the row index with the k-group: the 32 lanes of a warp (8 k-groups x 4 rows) then hit 32
+      // different banks, and groups of 4 rows stay contiguous for the 128-bit reads below
+      const int srow = lrow ^ (kg << 2);
+      As[buf][kg * 4 + 0][srow] = areg[i].x;
+      As[buf][kg * 4 + 1][srow] = areg[i].y;
+      As[buf][kg * 4 + 2][srow] = areg[i].z;
+      As[buf][kg * 4 + 3][srow] = areg[i].w;
     }
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(256) project_f32_kernel(const float* __restric
     if (item + 1 < total) prefetch(item + 1);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][(ty * 4) ^ ((k >> 2) << 2)]);
       const float4 b = *reinterpret_cast<const float4*>(&Vs[buf][k][tx * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
