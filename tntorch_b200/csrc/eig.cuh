@@ -98,7 +98,7 @@ inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>
     TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, *Xio, b, false,
                                                          reinterpret_cast<double*>(w.partial), w.S, b, 1.0, nullptr, 0,
                                                          0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
-    const size_t smem = (size_t)2 * b * b * sizeof(double);
+    const size_t smem = (size_t)2 * b * (b | 1) * sizeof(double);
     const bool fits = smem <= (size_t)180 * 1024;
     static bool attr_set = false;
     if (!attr_set) {

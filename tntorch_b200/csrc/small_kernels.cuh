@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
                                                          TB* __restrict__ T, int* flag, int use_smem) {
   extern __shared__ __align__(16) unsigned char chol_smem_raw[];
   __shared__ double s_d[JACOBI_MAX_N];
+  __shared__ double s_piv[JACOBI_MAX_N];
+  const int ld = b | 1;  // odd leading dimension: column walks (stride ld) spread over the banks
   double* L = use_smem ? reinterpret_cast<double*>(chol_smem_raw) : scratch;
-  double* Li = L + (size_t)b * b;
+  double* Li = L + (size_t)b * ld;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < b; i += nt) {
     const double v = S[(size_t)i * b + i];
@@ -181,15 +183,14 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
   __syncthreads();
   for (int idx = tid; idx < b * b; idx += nt) {
     const int i = idx / b, j = idx % b;
-    L[idx] = (j <= i) ? S[idx] * s_d[i] * s_d[j] : 0.0;
-    Li[idx] = 0.0;
+    L[(size_t)i * ld + j] = (j <= i) ? S[idx] * s_d[i] * s_d[j] : 0.0;
+    Li[(size_t)i * ld + j] = 0.0;
   }
   __syncthreads();
   // right-looking Cholesky with ONE barrier per column: the trailing update uses the unscaled column k and
   // 1/pivot; column k is final after step k, so its scaling by 1/sqrt(pivot) is deferred to a single pass.
-  __shared__ double s_piv[JACOBI_MAX_N];
   for (int k = 0; k < b; ++k) {
-    double piv = L[(size_t)k * b + k];  // broadcast read
+    double piv = L[(size_t)k * ld + k];  // broadcast read
     if (!(piv > 1e-11)) {
       if (tid == 0) *flag = 1;
       piv = 1e-11;
@@ -197,29 +198,31 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
     if (tid == 0) s_piv[k] = piv;
     const double ipiv = 1.0 / piv;
     const int rem = b - k - 1;
-    for (int idx = tid; idx < rem * rem; idx += nt) {
-      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
-      if (j <= i) L[(size_t)i * b + j] -= L[(size_t)i * b + k] * L[(size_t)j * b + k] * ipiv;
+    // rows i > k are dealt round-robin to the warps, the lanes walk j = k+1..i
+    for (int i = k + 1 + (tid >> 5); i < b; i += (nt >> 5)) {
+      const double lik = L[(size_t)i * ld + k] * ipiv;
+      for (int j = k + 1 + (tid & 31); j <= i; j += 32) L[(size_t)i * ld + j] -= lik * L[(size_t)j * ld + k];
     }
+    (void)rem;
     __syncthreads();
   }
   for (int idx = tid; idx < b * b; idx += nt) {
     const int i = idx / b, k = idx % b;
-    if (k < i) L[idx] *= rsqrt(s_piv[k]);
-    else if (k == i) L[idx] = sqrt(s_piv[k]);
+    if (k < i) L[(size_t)i * ld + k] *= rsqrt(s_piv[k]);
+    else if (k == i) L[(size_t)i * ld + k] = sqrt(s_piv[k]);
   }
   __syncthreads();
   // L^{-1}: one warp per column j (forward substitution, the inner sum split over the lanes)
   {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     for (int j = warp; j < b; j += nwarps) {
-      if (lane == 0) Li[(size_t)j * b + j] = 1.0 / L[(size_t)j * b + j];
+      if (lane == 0) Li[(size_t)j * ld + j] = 1.0 / L[(size_t)j * ld + j];
       __syncwarp();
       for (int i = j + 1; i < b; ++i) {
         double acc = 0.0;
-        for (int k = j + lane; k < i; k += 32) acc = fma(L[(size_t)i * b + k], Li[(size_t)k * b + j], acc);
+        for (int k = j + lane; k < i; k += 32) acc = fma(L[(size_t)i * ld + k], Li[(size_t)k * ld + j], acc);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) Li[(size_t)i * b + j] = -acc / L[(size_t)i * b + i];
+        if (lane == 0) Li[(size_t)i * ld + j] = -acc / L[(size_t)i * ld + i];
         __syncwarp();
       }
     }
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
   __syncthreads();
   for (int idx = tid; idx < b * b; idx += nt) {
     const int i = idx / b, j = idx % b;
-    T[idx] = (TB)((j >= i) ? s_d[i] * Li[(size_t)j * b + i] : 0.0);
+    T[idx] = (TB)((j >= i) ? s_d[i] * Li[(size_t)j * ld + i] : 0.0);
   }
 }
 
