@@ -105,6 +105,21 @@ int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double del
                       int32_t* rank_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * CP decomposition by alternating least squares.
+ * Replaces: tn.Tensor(data, ranks_cp=R, max_iter=, tol=)  tensor.py:210-400 (HOSVD init 217-277, ALS sweeps
+ *           323-361 with the MTTKRP of 355-357 and the lstsq of 358-360, stopping rule 373-381).
+ *   factors      output, factor n (shape[n] x R, row-major) at element offset factor_offsets_host[n];
+ *                capacity from tnb_cp_als_factors_capacity()
+ *   errors_host  max_iter doubles: relative error after each sweep;  *iters_host: sweeps performed
+ *   tol          stop when errors[-2] - errors[-1] < tol (pass -INFINITY for a fixed sweep count)
+ * ------------------------------------------------------------------------------------------ */
+int64_t tnb_cp_als_factors_capacity(int ndim, const int64_t* shape, int32_t R, int64_t* factor_offsets_host);
+size_t tnb_cp_als_workspace_bytes(int dtype, int ndim, const int64_t* shape, int32_t R);
+int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int32_t R, int32_t max_iter, double tol,
+               void* workspace, size_t workspace_bytes, void* factors, int64_t factors_capacity, double* errors_host,
+               int32_t* iters_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Building blocks (exposed for tests, profiling and the Python shim).
  * ------------------------------------------------------------------------------------------ */
 /* G (n x n, fp64) = A^T A for A (rows x n), dtype f32/f64; fp64 accumulation on CUDA cores.

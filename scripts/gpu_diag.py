@@ -24,8 +24,8 @@ if which in ("all", "blocks"):
         print("gram generic", shape, "relerr", ((G-ref).abs().max()/ref.abs().max()).item(), flush=True)
     for n in (64, 128, 256):
         A = torch.randn(4*n, n, dtype=torch.float64, device="cuda"); G = A.T @ A
-        w, V = ops.eigh_jacobi(G); wr = torch.linalg.eigvalsh(G).flip(0)
-        print("jacobi", n, "eigerr", ((w-wr).abs().max()/wr[0]).item(), "orth", (V.T@V-torch.eye(n,device='cuda',dtype=torch.float64)).abs().max().item(),
+        w, V, sw = ops.eigh_jacobi(G, return_sweeps=True); wr = torch.linalg.eigvalsh(G).flip(0)
+        print("jacobi", n, "sweeps", sw, "eigerr", ((w-wr).abs().max()/wr[0]).item(), "orth", (V.T@V-torch.eye(n,device='cuda',dtype=torch.float64)).abs().max().item(),
               "ms", t_ms(lambda: ops.eigh_jacobi(G)), flush=True)
 
 if which in ("all", "tc"):

@@ -1,0 +1,59 @@
+"""-m gpu: CP-ALS through the drop-in API against the fp64 reference (golden vectors, fixed sweep count;
+SURVEY §0.5: the reference's own fp32 ALS collapses, so parity is taken against fp64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cp_full(factors):
+    letters = "abcdefgh"[: len(factors)]
+    return np.einsum(",".join(f"{l}r" for l in letters) + "->" + letters, *[f.double().cpu().numpy() for f in factors])
+
+
+@pytest.mark.parametrize("name", list(cases.CP_CASES))
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_cp_als_matches_fp64_reference(name, dtype):
+    import tntorch_b200 as tnb
+
+    g = np.load(os.path.join(GOLD, "cp_als.npz"))
+    spec = cases.CP_CASES[name]
+    X = cases.make_cp_dense(spec)
+    t = tnb.Tensor(torch.as_tensor(X).to(dtype).cuda(), ranks_cp=spec["R"], max_iter=spec["sweeps"], tol=float("-inf"))
+    assert [tuple(c.shape) for c in t.cores] == [(s, spec["R"]) for s in spec["shape"]]
+    assert t.cores[0].dtype == dtype
+    err = np.linalg.norm(X - _cp_full(t.cores)) / np.linalg.norm(X)
+    ref = float(g[f"{name}/relerr"])
+    assert abs(err - ref) <= (1e-5 if dtype == torch.float64 else 1e-4), (err, ref)
+    # Tensor.torch() on CP cores reproduces the same reconstruction (tensor.py:1666-1680)
+    assert np.abs(t.torch().double().cpu().numpy() - _cp_full(t.cores)).max() <= 1e-4 * np.abs(X).max()
+
+
+def test_cp_als_error_trace_and_stopping():
+    from tntorch_b200 import ops
+
+    spec = cases.CP_CASES["cp_16x4_R5"]
+    X = torch.as_tensor(cases.make_cp_dense(spec)).cuda()
+    fac, info = ops.cp_als(X, 5, max_iter=25, tol=1e-4, return_info=True)
+    errs = info["errors"]
+    assert 2 <= info["iters"] <= 25 and len(errs) == info["iters"]
+    assert errs[-2] - errs[-1] < 1e-4 or info["iters"] == 25  # tensor.py:380-381
+    true = np.linalg.norm(X.cpu().numpy() - _cp_full(fac)) / np.linalg.norm(X.cpu().numpy())
+    assert abs(errs[-1] - true) < 1e-6  # the Gram-based error formula equals the reconstruction error
+
+
+def test_cp_als_rank_larger_than_mode():
+    """I_n < R: missing HOSVD columns are filled pseudo-randomly (tensor.py:258-272)."""
+    from tntorch_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    fs = [torch.randn(s, 6, generator=g, dtype=torch.float64) for s in (4, 9, 8)]
+    X = torch.einsum("ar,br,cr->abc", *fs).cuda()
+    fac, info = ops.cp_als(X, 6, max_iter=60, tol=float("-inf"), return_info=True)
+    assert info["errors"][-1] < 0.2

@@ -35,6 +35,9 @@ struct GemmArgs {
   int64_t lde;
   TAcc gamma;
   int symmetric;  // only tiles with tn >= tm (A and B describe the same matrix)
+  // batched accumulation: C = sum_b A_b * B_b with A_b = A + b*batch_stride_a (same K each); split z then owns
+  // batches [z*batches_per_split, ...) instead of a K range.  nbatch == 0: plain GEMM.
+  int64_t nbatch, batches_per_split, batch_stride_a, batch_stride_b;
 };
 
 template <typename TA, typename TB, typename TAcc, typename TC, bool A_KMAJ, bool B_KMAJ, bool DIRECT>
@@ -44,8 +47,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
   const int tm = blockIdx.x, tn = blockIdx.y, z = blockIdx.z;
   if (p.symmetric && tn < tm) return;
   const int64_t m0 = (int64_t)tm * GEMM_BM, n0 = (int64_t)tn * GEMM_BN;
-  const int64_t kbeg = (int64_t)z * p.k_per_split;
-  const int64_t kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
+  int64_t kbeg = (int64_t)z * p.k_per_split;
+  int64_t kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
+  int64_t b0 = 0, b1 = 1;
+  if (p.nbatch > 0) {
+    kbeg = 0;
+    kend = p.K;
+    b0 = (int64_t)z * p.batches_per_split;
+    b1 = b0 + p.batches_per_split < p.nbatch ? b0 + p.batches_per_split : p.nbatch;
+  }
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   TAcc acc[4][4];
@@ -54,6 +64,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
 
+  for (int64_t bb = b0; bb < b1; ++bb) {
+  const TA* Ab = p.A + bb * p.batch_stride_a;
+  const TB* Bb = p.B + bb * p.batch_stride_b;
   for (int64_t k0 = kbeg; k0 < kend; k0 += GEMM_BK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -68,7 +81,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
       }
       const int64_t gm = m0 + mm, gk = k0 + kk;
       TAcc v = TAcc(0);
-      if (gm < p.M && gk < kend) v = (TAcc)(A_KMAJ ? p.A[gm * p.lda + gk] : p.A[gk * p.lda + gm]);
+      if (gm < p.M && gk < kend) v = (TAcc)(A_KMAJ ? Ab[gm * p.lda + gk] : Ab[gk * p.lda + gm]);
       As[kk][mm] = v;
     }
 #pragma unroll
@@ -84,7 +97,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
       }
       const int64_t gn = n0 + nn, gk = k0 + kk;
       TAcc v = TAcc(0);
-      if (gn < p.N && gk < kend) v = (TAcc)(B_KMAJ ? p.B[gn * p.ldb + gk] : p.B[gk * p.ldb + gn]);
+      if (gn < p.N && gk < kend) v = (TAcc)(B_KMAJ ? Bb[gn * p.ldb + gk] : Bb[gk * p.ldb + gn]);
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -101,6 +114,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
+  }
   }
 
 #pragma unroll
@@ -227,6 +241,43 @@ inline int gemm_splitk(const GemmPlan& pl, int64_t M, int64_t N, int64_t K, cons
   int blocks = (int)(ceil_div<int64_t>(total, 256) < 4096 ? ceil_div<int64_t>(total, 256) : 4096);
   gemm_finalize_kernel<TAcc, TC, TC2><<<blocks, 256, 0, st>>>(partial, pl.splits, M, N, C, ldc, alpha, D, ldd, beta, E,
                                                               lde, gamma, symmetric ? 1 : 0, C2, ldc2);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+// C = sum_{b < nbatch} A_b B_b (same shapes, A_b = A + b*stride): split over batches, deterministic reduce.
+// partial must hold plan_batched(...).partial_elems TAcc's.
+inline GemmPlan plan_batched(int64_t M, int64_t N, int64_t nbatch, bool symmetric) {
+  GemmPlan pl;
+  const int64_t tm = ceil_div<int64_t>(M, GEMM_BM), tn = ceil_div<int64_t>(N, GEMM_BN);
+  int64_t tiles = symmetric ? tm * (tn + 1) / 2 : tm * tn;
+  int sms = device_info().valid ? device_info().sm_count : 148;
+  int64_t s = ceil_div<int64_t>(4 * (int64_t)sms, tiles);
+  if (s > nbatch) s = nbatch;
+  if (s > 256) s = 256;
+  if (s < 1) s = 1;
+  const int64_t bps = ceil_div<int64_t>(nbatch, s);
+  s = ceil_div<int64_t>(nbatch, bps);
+  pl.splits = (int)s;
+  pl.k_per_split = bps;  // re-used as batches per split
+  pl.partial_elems = (size_t)s * (size_t)M * (size_t)N;
+  return pl;
+}
+
+template <typename TA, typename TB, typename TAcc, typename TC>
+inline int gemm_batched_sum(const GemmPlan& pl, int64_t M, int64_t N, int64_t K, int64_t nbatch, const TA* A, int64_t lda,
+                            bool a_kmaj, int64_t bsa, const TB* B, int64_t ldb, bool b_kmaj, int64_t bsb, TAcc* partial,
+                            TC* C, int64_t ldc, bool symmetric, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return TNB_OK;
+  GemmArgs<TA, TB, TAcc, TC> a{};
+  a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb;
+  a.k_per_split = K; a.partial = partial; a.C = nullptr; a.symmetric = symmetric ? 1 : 0;
+  a.nbatch = nbatch; a.batches_per_split = pl.k_per_split; a.batch_stride_a = bsa; a.batch_stride_b = bsb;
+  TNB_TRY((launch_gemm_tiles<TA, TB, TAcc, TC, false>(a, a_kmaj, b_kmaj, pl.splits, st)));
+  const int64_t total = M * N;
+  int blocks = (int)(ceil_div<int64_t>(total, 256) < 4096 ? ceil_div<int64_t>(total, 256) : 4096);
+  gemm_finalize_kernel<TAcc, TC, TC><<<blocks, 256, 0, st>>>(partial, pl.splits, M, N, C, ldc, (TAcc)1, nullptr, 0, (TAcc)0,
+                                                            nullptr, 0, (TAcc)0, symmetric ? 1 : 0, (TC*)nullptr, 0);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
 }

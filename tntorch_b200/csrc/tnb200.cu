@@ -8,6 +8,7 @@
 #include "gram_tc.cuh"
 #include "sweep.cuh"
 #include "round_impl.cuh"
+#include "cp_als.cuh"
 
 using namespace tnb;
 
@@ -200,6 +201,45 @@ int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double del
   return truncated_svd_impl<double>(ar, false, static_cast<const double*>(M), m, n, delta, eps, rmax, left_ortho,
                                     static_cast<double*>(left), static_cast<double*>(right), rank_host,
                                     as_stream(stream));
+}
+
+// ------------------------------------------------------------------ CP-ALS
+int64_t tnb_cp_als_factors_capacity(int ndim, const int64_t* shape, int32_t R, int64_t* factor_offsets_host) {
+  CpDims d;
+  if (make_cp_dims(ndim, shape, R, d) != TNB_OK) return -1;
+  if (factor_offsets_host)
+    for (int n = 0; n < ndim; ++n) factor_offsets_host[n] = d.foff[n];
+  return d.ftotal;
+}
+
+size_t tnb_cp_als_workspace_bytes(int dtype, int ndim, const int64_t* shape, int32_t R) {
+  CpDims d;
+  if (check_dtype(dtype) != TNB_OK || make_cp_dims(ndim, shape, R, d) != TNB_OK) return 0;
+  ArenaSizer ar;
+  int rc;
+  if (dtype == TNB_F32)
+    rc = cp_als_impl<float>(ar, true, nullptr, d, R, 1, 0.0, nullptr, nullptr, nullptr, 0);
+  else
+    rc = cp_als_impl<double>(ar, true, nullptr, d, R, 1, 0.0, nullptr, nullptr, nullptr, 0);
+  return rc == TNB_OK ? with_slack(ar.off) : 0;
+}
+
+int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int32_t R, int32_t max_iter, double tol,
+               void* workspace, size_t workspace_bytes, void* factors, int64_t factors_capacity, double* errors_host,
+               int32_t* iters_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!data || !shape || !workspace || !factors) return fail(TNB_ERR_INVALID, "tnb_cp_als: null argument");
+  if (max_iter < 0) return fail(TNB_ERR_INVALID, "tnb_cp_als: max_iter < 0");
+  CpDims d;
+  TNB_TRY(make_cp_dims(ndim, shape, R, d));
+  if (factors_capacity < d.ftotal) return fail(TNB_ERR_WORKSPACE, "tnb_cp_als: factor buffer too small");
+  Arena ar(workspace, workspace_bytes);
+  if (dtype == TNB_F32)
+    return cp_als_impl<float>(ar, false, static_cast<const float*>(data), d, R, max_iter, tol,
+                              static_cast<float*>(factors), errors_host, iters_host, as_stream(stream));
+  return cp_als_impl<double>(ar, false, static_cast<const double*>(data), d, R, max_iter, tol,
+                             static_cast<double*>(factors), errors_host, iters_host, as_stream(stream));
 }
 
 // ------------------------------------------------------------------ building blocks

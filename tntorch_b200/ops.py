@@ -232,6 +232,36 @@ def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=T
     return left[: m * r].view(m, r), right[: r * n].view(r, n)
 
 
+def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, return_info: bool = False):
+    """CP-ALS on the device (tn.Tensor(data, ranks_cp=R, max_iter=, tol=), tensor.py:210-400).
+    Returns the list of factor matrices [I_n, R]."""
+    _require_cuda(data, "cp_als")
+    data = data.contiguous()
+    code = _dtype_code(data)
+    N = data.dim()
+    shape = list(data.shape)
+    L = lib()
+    sh = i64(shape)
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_cp_als_factors_capacity(N, sh, int(R), offs)
+    if cap < 0:
+        check(_lib.ERR_INVALID if N >= 2 else _lib.ERR_UNSUPPORTED)
+    wsb = L.tnb_cp_als_workspace_bytes(code, N, sh, int(R))
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, data.device)
+    fac = torch.empty(int(cap), dtype=data.dtype, device=data.device)
+    errs = (C.c_double * max(int(max_iter), 1))()
+    iters = (C.c_int32 * 1)()
+    with torch.cuda.device(data.device):
+        check(L.tnb_cp_als(code, _ptr(data), N, sh, int(R), int(max_iter), float(tol), _ptr(ws), ws.numel(), _ptr(fac), cap,
+                           errs, iters, _stream()))
+    factors = [fac[offs[n]: offs[n] + shape[n] * R].view(shape[n], R) for n in range(N)]
+    if return_info:
+        return factors, dict(errors=[errs[i] for i in range(iters[0])], iters=int(iters[0]))
+    return factors
+
+
 def gram(A: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
     """fp64 Gram matrix A^T A of a (rows x n) matrix; tensorcore=True uses the tcgen05/TMA kernel (fp32 only)."""
     _require_cuda(A, "gram")
@@ -286,7 +316,7 @@ def project(A: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
     return Cc
 
 
-def eigh_jacobi(G: torch.Tensor):
+def eigh_jacobi(G: torch.Tensor, return_sweeps: bool = False):
     _require_cuda(G, "eigh_jacobi")
     G = G.contiguous().double()
     n = G.shape[0]
@@ -299,6 +329,10 @@ def eigh_jacobi(G: torch.Tensor):
     ws = _ws(wsb, G.device)
     with torch.cuda.device(G.device):
         check(L.tnb_eigh_jacobi(_ptr(G), n, _ptr(w), _ptr(V), _ptr(ws), ws.numel(), _stream()))
+    if return_sweeps:  # the kernel leaves its sweep count right behind the (256-byte aligned) scratch matrices
+        npad = n + (n & 1)
+        off = (2 * npad * (npad + 8) * 8 + 255) // 256 * 256
+        return w, V, int(ws[off: off + 4].view(torch.int32).item())
     return w, V
 
 

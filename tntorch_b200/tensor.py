@@ -48,20 +48,20 @@ class Tensor(object):
     ):
         assert algorithm in ("svd", "eig")  # both map onto the same Gram/eigen kernels
         self.batch = batch
-        if ranks_cp is not None or ranks_tucker is not None:
+        if ranks_tucker is not None:
             raise NotImplementedError(
-                "tntorch_b200 covers the TT decomposition/rounding path (SURVEY.md §8); CP-ALS and Tucker "
-                "rounding are listed as next rows and are not built yet"
+                "tntorch_b200 covers the TT / CP decomposition and TT rounding path (SURVEY.md §8); Tucker "
+                "rounding is listed as a next row and is not built yet"
             )
         if isinstance(data, (list, tuple)):  # explicit cores (tensor.py:163-192)
             min_dim, max_dim = (3, 4) if batch else (2, 3)
             if not all(min_dim <= d.dim() <= max_dim for d in data):
                 raise ValueError("All tensor cores must have 2 (for CP) or 3 (for TT) dimensions")
-            if any(d.dim() != max_dim for d in data):
-                raise NotImplementedError("CP cores are outside the TT path built here")
-            d1 = 1 if batch else 0
-            for n in range(len(data) - 1):
-                if data[n].shape[-1] != data[n + 1].shape[d1]:
+            d1, d2 = (1, 2) if batch else (0, 1)
+            for n in range(len(data) - 1):  # tensor.py:177-191
+                if (data[n + 1].dim() == max_dim and data[n].shape[-1] != data[n + 1].shape[d1]) or (
+                    data[n + 1].dim() == min_dim and data[n].shape[-1] != data[n + 1].shape[d2]
+                ):
                     raise ValueError("Core ranks do not match")
             dev = _default_device(device if device is not None else (data[0].device if data[0].is_cuda else None))
             self.cores = [c.to(dev) for c in data]
@@ -80,7 +80,18 @@ class Tensor(object):
             if eps is not None and ranks_tt is not None:
                 raise ValueError("Specify eps or ranks, but not both")  # tensor.py:436-438
             N = data.dim() - 1 if batch else data.dim()
-            if batch:
+            if ranks_cp is not None:  # CP-ALS (tensor.py:210-400)
+                if ranks_tt is not None:
+                    raise ValueError("ALS for CP-TT is not yet supported")
+                assert not hasattr(ranks_cp, "__len__")
+                if eps is not None:
+                    raise ValueError("Specify eps or ranks, but not both")
+                if batch:
+                    self.cores = [torch.stack(f, dim=0) for f in zip(*[
+                        ops.cp_als(data[b], ranks_cp, max_iter=max_iter, tol=tol) for b in range(data.shape[0])])]
+                else:
+                    self.cores = ops.cp_als(data, ranks_cp, max_iter=max_iter, tol=tol)
+            elif batch:
                 # the reference's batch mode: per-sample decomposition, rank = min(rmax, len(S)), no eps
                 per = [ops.ttsvd(data[b], rmax=ranks_tt, batch_mode=True) for b in range(data.shape[0])]
                 self.cores = [torch.stack([p[k] for p in per], dim=0) for k in range(N)]
@@ -111,7 +122,8 @@ class Tensor(object):
     @property
     def ranks_tt(self):
         d1 = 1 if self.batch else 0
-        return torch.tensor([self.cores[0].shape[d1]] + [c.shape[-1] for c in self.cores])
+        first = self.cores[0].shape[d1] if self.cores[0].dim() == (4 if self.batch else 3) else self.cores[0].shape[-1]
+        return torch.tensor([first] + [c.shape[-1] for c in self.cores])
 
     def numcoef(self):
         return sum(c.numel() for c in self.cores)
@@ -126,9 +138,19 @@ class Tensor(object):
     def torch(self):
         if self.batch:
             return torch.stack([Tensor([c[b] for c in self.cores]).torch() for b in range(self.cores[0].shape[0])])
-        f = torch.ones(1, self.cores[0].shape[0], dtype=self.cores[0].dtype, device=self.cores[0].device)
-        for c in self.cores:
-            f = (f @ c.reshape(c.shape[0], -1)).reshape(-1, c.shape[2])
+        c0 = self.cores[0]
+        r0 = c0.shape[0] if c0.dim() == 3 else c0.shape[1]
+        f = torch.ones(1, r0, dtype=c0.dtype, device=c0.device)
+        last = len(self.cores) - 1
+        for n, c in enumerate(self.cores):  # tensor.py:1666-1680
+            if c.dim() == 2:  # CP factor [I, R]
+                if n < last:
+                    f = torch.einsum("ai,bi->abi", f, c)
+                else:
+                    f = torch.einsum("ai,bi->ab", f, c)[..., None]
+            else:
+                f = torch.einsum("ai,ibj->abj", f, c)
+            f = f.reshape(-1, f.shape[-1])
         f = f.sum(dim=-1) if f.shape[-1] > 1 else f[..., 0]
         return f.reshape(list(self.shape))
 
