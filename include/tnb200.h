@@ -120,6 +120,26 @@ int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int3
                int32_t* iters_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * maxvol: dominant r x r submatrix of each of `nbatch` tall N x r fp64 matrices (row-major, contiguous batch).
+ * Replaces: py_maxvol(A, tol=1.05, max_iters=100)  tntorch/maxvol.py:114-170, called per TT core from tn.cross
+ *           (cross.py:399-402, 431-434) after a device->host copy; here everything stays on the device.
+ *   index_dev  nbatch x r int32 (device): selected rows      C_dev  nbatch x N x r (device): A inv(A[index]),
+ *              i.e. the interpolation core cross.py:403 recomputes with lstsq
+ *   iters_host optional nbatch ints (host): swap iterations used (forces a stream sync when given)
+ * ------------------------------------------------------------------------------------------ */
+size_t tnb_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r);
+int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t max_iters, void* workspace,
+               size_t workspace_bytes, int32_t* index_dev, double* C_dev, int32_t* iters_host, void* stream);
+
+/* Tall-skinny Householder QR of `nbatch` fp64 matrices (rows x n, row-major): Q (rows x min(rows,n)) explicit,
+ * optional R (min(rows,n) x n).  Warp-shuffle reflector kernels, one CTA per matrix.
+ * Replaces: torch.linalg.qr(V) before maxvol in tn.cross (cross.py:398, 430) and the QR of
+ * Tensor.left_orthogonalize (tensor.py:1816) for small cores. */
+size_t tnb_qr_workspace_bytes(int32_t nbatch, int32_t rows, int32_t n);
+int tnb_qr_householder(const double* A, int32_t nbatch, int32_t rows, int32_t n, void* workspace, size_t workspace_bytes,
+                       double* Q, double* R, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Building blocks (exposed for tests, profiling and the Python shim).
  * ------------------------------------------------------------------------------------------ */
 /* G (n x n, fp64) = A^T A for A (rows x n), dtype f32/f64; fp64 accumulation on CUDA cores.

@@ -170,3 +170,20 @@ CP_CASES = {
     "cp_16x4_R5": dict(shape=(16,) * 4, Rtrue=5, R=5, sweeps=10, noise=1e-2, seed=50, dtype="float64"),
     "cp_20x3_R8": dict(shape=(20, 18, 16), Rtrue=8, R=8, sweeps=8, noise=1e-3, seed=51, dtype="float64"),
 }
+
+# ---- TT-cross (seeded global NumPy/torch RNGs; function f(x) = 1 / (shift + sum_i x_i)) ----------------
+CROSS_CASES = {
+    "cfg5_32x6_r10": dict(N=6, I=32, lo=0.0, hi=1.0, shift=1.0, ranks_tt=10, max_iter=3, seed=60),
+    "adaptive_32x5": dict(N=5, I=32, lo=1.0, hi=32.0, shift=0.0, kickrank=3, eps=1e-6, max_iter=25, seed=61),
+    "small_10x3_r3": dict(N=3, I=10, lo=1.0, hi=10.0, shift=0.0, ranks_tt=3, max_iter=5, seed=62),
+}
+
+
+def cross_function(shift):
+    def f(*xs):
+        s = xs[0] * 0 + shift
+        for x in xs:
+            s = s + x
+        return 1.0 / s
+
+    return f

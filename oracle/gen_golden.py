@@ -122,8 +122,33 @@ def gen_cpals():
     np.savez_compressed(os.path.join(OUT, "cp_als.npz"), **out)
 
 
+def gen_cross():
+    out = {}
+    torch.set_default_dtype(torch.float64)
+    for name, spec in cases.CROSS_CASES.items():
+        np.random.seed(spec["seed"])
+        torch.manual_seed(spec["seed"])
+        domain = [torch.linspace(spec["lo"], spec["hi"], spec["I"], dtype=torch.float64) for _ in range(spec["N"])]
+        kw = {k: spec[k] for k in ("ranks_tt", "kickrank", "eps", "max_iter") if k in spec}
+        t, info = tn.cross(cases.cross_function(spec["shift"]), domain=domain, verbose=False, return_info=True,
+                           suppress_warnings=True, **kw)
+        full_err = None
+        if spec["I"] ** spec["N"] <= 40_000_000:
+            grids = torch.meshgrid(*domain, indexing="ij")
+            gt = cases.cross_function(spec["shift"])(*grids)
+            full_err = float(torch.norm(gt - t.torch()) / torch.norm(gt))
+            out[f"{name}/full_relerr"] = np.float64(full_err)
+        out[f"{name}/val_eps"] = np.float64(float(info["val_eps"]))
+        out[f"{name}/nsamples"] = np.int64(info["nsamples"])
+        out[f"{name}/Rs"] = np.asarray(info["Rs"], dtype=np.int64)
+        out[f"{name}/lset_last"] = np.asarray(info["lsets"][-1], dtype=np.int64)
+        print(name, float(info["val_eps"]), info["nsamples"], list(info["Rs"]), full_err, flush=True)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "cross.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp"]
+    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross"]
     if "ttsvd" in which:
         gen_ttsvd()
     if "round" in which:
@@ -134,3 +159,5 @@ if __name__ == "__main__":
         gen_maxvol()
     if "cp" in which:
         gen_cpals()
+    if "cross" in which:
+        gen_cross()

@@ -9,6 +9,8 @@
 #include "sweep.cuh"
 #include "round_impl.cuh"
 #include "cp_als.cuh"
+#include "maxvol.cuh"
+#include "qr.cuh"
 
 using namespace tnb;
 
@@ -240,6 +242,32 @@ int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int3
                               static_cast<float*>(factors), errors_host, iters_host, as_stream(stream));
   return cp_als_impl<double>(ar, false, static_cast<const double*>(data), d, R, max_iter, tol,
                              static_cast<double*>(factors), errors_host, iters_host, as_stream(stream));
+}
+
+// ------------------------------------------------------------------ maxvol
+size_t tnb_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r) {
+  if (nbatch < 1 || N < 1 || r < 1) return 0;
+  return maxvol_workspace_bytes(nbatch, N, r) + 256;
+}
+
+int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t max_iters, void* workspace,
+               size_t workspace_bytes, int32_t* index_dev, double* C_dev, int32_t* iters_host, void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !workspace || !index_dev || !C_dev) return fail(TNB_ERR_INVALID, "tnb_maxvol: null argument");
+  return maxvol_run(A, nbatch, N, r, tol, max_iters, workspace, workspace_bytes, index_dev, C_dev, iters_host,
+                    as_stream(stream));
+}
+
+size_t tnb_qr_workspace_bytes(int32_t nbatch, int32_t rows, int32_t n) {
+  if (nbatch < 1 || rows < 1 || n < 1) return 0;
+  return householder_qr_workspace_bytes(nbatch, rows, n) + 256;
+}
+
+int tnb_qr_householder(const double* A, int32_t nbatch, int32_t rows, int32_t n, void* workspace, size_t workspace_bytes,
+                       double* Q, double* R, void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !workspace || !Q) return fail(TNB_ERR_INVALID, "tnb_qr_householder: null argument");
+  return householder_qr_run(A, nbatch, rows, n, workspace, workspace_bytes, Q, R, as_stream(stream));
 }
 
 // ------------------------------------------------------------------ building blocks

@@ -262,6 +262,49 @@ def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, re
     return factors
 
 
+def maxvol(A: torch.Tensor, tol: float = 1.05, max_iters: int = 100, return_iters: bool = False):
+    """Device maxvol (tntorch/maxvol.py:114-170).  A: [N, r] or a batch [B, N, r].  Returns (index int32 [.., min(N,r)],
+    C [.., N, r] = A inv(A[index])) as device tensors; nothing is copied to the host."""
+    _require_cuda(A, "maxvol")
+    batched = A.dim() == 3
+    A3 = (A if batched else A[None]).contiguous().double()
+    B, N, r = A3.shape
+    L = lib()
+    ws = _ws(L.tnb_maxvol_workspace_bytes(B, N, r), A.device)
+    index = torch.empty(B, r, dtype=torch.int32, device=A.device)
+    Cm = torch.empty(B, N, r, dtype=torch.float64, device=A.device)
+    iters = (C.c_int32 * B)() if return_iters else None
+    with torch.cuda.device(A.device):
+        check(L.tnb_maxvol(_ptr(A3), B, N, r, float(tol), int(max_iters), _ptr(ws), ws.numel(), _ptr(index), _ptr(Cm), iters,
+                           _stream()))
+    if N <= r:  # maxvol.py:126-127
+        index, Cm = index[:, :N], Cm[:, :, :N]
+    if not batched:
+        index, Cm = index[0], Cm[0]
+    if return_iters:
+        return index, Cm, [int(x) for x in iters]
+    return index, Cm
+
+
+def qr(A: torch.Tensor, return_r: bool = False):
+    """Householder QR on the device (torch.linalg.qr semantics, reduced): A [rows, n] or batch [B, rows, n], fp64."""
+    _require_cuda(A, "qr")
+    batched = A.dim() == 3
+    A3 = (A if batched else A[None]).contiguous().double()
+    B, rows, n = A3.shape
+    k = min(rows, n)
+    L = lib()
+    ws = _ws(L.tnb_qr_workspace_bytes(B, rows, n), A.device)
+    Q = torch.empty(B, rows, k, dtype=torch.float64, device=A.device)
+    R = torch.empty(B, k, n, dtype=torch.float64, device=A.device) if return_r else None
+    with torch.cuda.device(A.device):
+        check(L.tnb_qr_householder(_ptr(A3), B, rows, n, _ptr(ws), ws.numel(), _ptr(Q), _ptr(R), _stream()))
+    if not batched:
+        Q = Q[0]
+        R = R[0] if return_r else None
+    return (Q, R) if return_r else Q
+
+
 def gram(A: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
     """fp64 Gram matrix A^T A of a (rows x n) matrix; tensorcore=True uses the tcgen05/TMA kernel (fp32 only)."""
     _require_cuda(A, "gram")
