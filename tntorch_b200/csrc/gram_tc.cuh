@@ -332,19 +332,17 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+inline PFN_encodeTiled load_encode_tiled() {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+      q == cudaDriverEntryPointSuccess)
+    return reinterpret_cast<PFN_encodeTiled>(f);
+  cudaGetLastError();
+  return nullptr;
+}
 inline PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(f);
-    else
-      cudaGetLastError();
-  }
+  static PFN_encodeTiled fn = load_encode_tiled();  // thread-safe one-time initialisation
   return fn;
 }
 
