@@ -161,6 +161,11 @@ int tnb_atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t
 /* C (rows x r) = A (rows x n) * V (n x r), same dtype throughout (fp32: FFMA, fp32 accumulate).
  * Replaces: `M @ left` round.py:181 / einsum absorb tensor.py:2081-2083. */
 int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream);
+/* The same projection on the tcgen05 tensor cores at fp32 accuracy (3xTF32 split: A_hi V_hi + A_hi V_lo + A_lo V_hi),
+ * fp32 only, r <= 64, n % 4 == 0, rows >= 128.  Used by the sweep for the large carries. */
+size_t tnb_project_tc_workspace_bytes(int64_t n, int32_t r);
+int tnb_project_tc_f32(const float* A, int64_t rows, int64_t n, const float* V, int32_t r, float* C, void* workspace,
+                       size_t workspace_bytes, void* stream);
 /* Symmetric eigendecomposition of a PSD matrix G (n x n fp64): all eigenpairs by one-CTA parallel
  * Jacobi (n <= 256), eigenvalues descending in w, eigenvectors in the columns of V (row-major n x n).
  * Replaces: torch.linalg.eigh round.py:114 / the U,S of torch.linalg.svd round.py:96. */

@@ -60,3 +60,21 @@ def test_atb_tc_matches_fp64(shape):
     Bi = torch.randint(-8, 9, (K, n), generator=g).float().cuda()
     Ci = ops.atb_tensorcore(Ai, Bi)
     assert torch.equal(Ci.double(), Ai.double().T @ Bi.double())
+
+
+@pytest.mark.parametrize("shape", [(16384, 64, 32), (20000, 2048, 32), (4096 + 77, 96, 17), (70000, 64, 64), (1000, 32, 8)])
+def test_project_tc_fp32_accuracy(shape):
+    """3xTF32 projection on the tensor cores keeps fp32 accuracy (a 1xTF32 product would be ~2^-11)."""
+    from tntorch_b200 import ops
+
+    rows, n, r = shape
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(rows, n, generator=g).cuda()
+    V = torch.randn(n, r, generator=g).cuda()
+    C = ops.project(A, V, tensorcore=True)
+    ref = A.double() @ V.double()
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-6, err
+    Cf = ops.project(A, V)  # FFMA kernel for comparison
+    errf = (Cf.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 20 * max(errf, 1e-7)

@@ -19,13 +19,22 @@
 #include "small_kernels.cuh"
 #include "gram_tc.cuh"
 #include "project.cuh"
+#include "project_tc.cuh"
 
 namespace tnb {
 
 // C (rows x r) = A (rows x n) * V (n x r) in the data precision: streaming FFMA kernel for fp32 when the
 // shape allows, generic tiled GEMM otherwise.
+constexpr int64_t PROJ_TC_MIN_ROWS = 16384;
+inline bool project_use_tc(int64_t rows, int64_t n, int64_t r, const void* A, const void* C) {
+  return rows >= PROJ_TC_MIN_ROWS && project_tc_shape_ok(rows, n, r, A, C);
+}
 template <typename T>
-inline int project_any(const T* A, int64_t rows, int64_t n, const T* V, int64_t r, T* C, cudaStream_t st) {
+inline int project_any(const T* A, int64_t rows, int64_t n, const T* V, int64_t r, T* C, cudaStream_t st,
+                       void* tc_ws = nullptr, size_t tc_ws_bytes = 0) {
+  if (std::is_same<T, float>::value && tc_ws && tc_path_available() && project_use_tc(rows, n, r, A, C))
+    return project_tc_f32(reinterpret_cast<const float*>(A), rows, n, reinterpret_cast<const float*>(V), (int)r,
+                          reinterpret_cast<float*>(C), tc_ws, tc_ws_bytes, st);
   if (std::is_same<T, float>::value && project_f32_fast_ok(rows, n, r, A, C))
     return project_f32_fast(reinterpret_cast<const float*>(A), rows, n, reinterpret_cast<const float*>(V), (int)r,
                             reinterpret_cast<float*>(C), st);
@@ -241,6 +250,13 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   TNB_TRY(eig_carve<TBk>(ar, L, kcap, have_rmax, ew));
   if (ew.chfsi && std::is_same<TBk, float>::value) Gf = reinterpret_cast<float*>(ew.Gb);
   T* fac = ar.template take<T>((size_t)L * (size_t)kcap);  // V_r or U_r/s
+  void* ptc_ws = nullptr;
+  size_t ptc_bytes = 0;
+  if (cx.allow_tc && std::is_same<T, float>::value && tall && rows >= PROJ_TC_MIN_ROWS && kcap <= PT_MAX_N && n % 4 == 0 &&
+      n >= 32) {
+    ptc_bytes = project_tc_workspace_bytes(n, kcap);
+    ptc_ws = ar.template take<char>(ptc_bytes);
+  }
   if (dry) return TNB_OK;
   if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "workspace too small (need > %zu bytes)", ar.off);
   Prof& prof = Prof::get();
@@ -275,7 +291,7 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
     TNB_LAUNCH_CHECK();
     scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)n, (int)rank, ew.w, fac, 0, 0);
     TNB_LAUNCH_CHECK();
-    TNB_TRY(project_any<T>(C, rows, n, fac, rank, Cn, st));
+    TNB_TRY(project_any<T>(C, rows, n, fac, rank, Cn, st, ptc_ws, ptc_bytes));
   } else {
     // core = diag(1/s) U_r^T C (rank x n);  Cn = U_r diag(s)
     scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, fac, 1, 0);

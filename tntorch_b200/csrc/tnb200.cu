@@ -332,6 +332,18 @@ int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V
                              static_cast<double*>(C), st);
 }
 
+size_t tnb_project_tc_workspace_bytes(int64_t n, int32_t r) {
+  if (n < 32 || n % 4 != 0 || r < 1 || r > PT_MAX_N) return 0;
+  return project_tc_workspace_bytes(n, r) + 256;
+}
+
+int tnb_project_tc_f32(const float* A, int64_t rows, int64_t n, const float* V, int32_t r, float* C, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !V || !C || !workspace) return fail(TNB_ERR_INVALID, "tnb_project_tc_f32: null argument");
+  return project_tc_f32(A, rows, n, V, r, C, workspace, workspace_bytes, as_stream(stream));
+}
+
 size_t tnb_eigh_workspace_bytes(int32_t n) {
   if (n < 1 || n > JACOBI_MAX_N) return 0;
   return align_up(jacobi_scratch_doubles(n) * sizeof(double)) + 256;

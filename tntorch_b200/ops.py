@@ -347,13 +347,22 @@ def atb_tensorcore(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, D: Opti
     return out
 
 
-def project(A: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+def project(A: torch.Tensor, V: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
     _require_cuda(A, "project")
     A, V = A.contiguous(), V.contiguous()
     rows, n = A.shape
     assert V.shape[0] == n and V.dtype == A.dtype
     r = V.shape[1]
     Cc = torch.empty(rows, r, dtype=A.dtype, device=A.device)
+    if tensorcore:
+        L = lib()
+        wsb = L.tnb_project_tc_workspace_bytes(n, r)
+        if wsb == 0 or A.dtype != torch.float32:
+            check(_lib.ERR_UNSUPPORTED)
+        ws = _ws(wsb, A.device)
+        with torch.cuda.device(A.device):
+            check(L.tnb_project_tc_f32(_ptr(A), rows, n, _ptr(V), r, _ptr(Cc), _ptr(ws), ws.numel(), _stream()))
+        return Cc
     with torch.cuda.device(A.device):
         check(lib().tnb_project(_dtype_code(A), _ptr(A), rows, n, _ptr(V), r, _ptr(Cc), _stream()))
     return Cc
