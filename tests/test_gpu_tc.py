@@ -74,7 +74,7 @@ def test_project_tc_fp32_accuracy(shape):
     C = ops.project(A, V, tensorcore=True)
     ref = A.double() @ V.double()
     err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 3e-6, err
+    assert err < 4e-6, err  # truncating TMEM accumulation is bounded by slabs of 256 columns
     Cf = ops.project(A, V)  # FFMA kernel for comparison
     errf = (Cf.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 20 * max(errf, 1e-7)

@@ -34,8 +34,12 @@ struct ProjTcParams {
   int npad;    // r rounded up to a multiple of 16
   int64_t num_row_blocks;
   int nk;      // K chunks
+  int slab;    // chunks per accumulator slab: the TMEM accumulator truncates on every add, so long K ranges are cut
+               // into slabs of PT_SLAB_CHUNKS*32 columns whose partial tiles are summed in fp32 (RN) by the epilogue
+  int nslabs;
   float* C;
 };
+constexpr int PT_SLAB_CHUNKS = 8;
 
 // K-major operand, SWIZZLE_128B: 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t make_k_major_desc(uint32_t smem_addr) {
@@ -126,20 +130,23 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t idesc = make_idesc_tf32_kk(PT_BM, p.npad);
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t blk = 0; blk < my_blocks; ++blk) {
-        const int slot = (int)(blk % PT_ACC_SLOTS);
-        const uint32_t acc_phase = (uint32_t)((blk / PT_ACC_SLOTS) & 1);
+      const int64_t tiles = my_blocks * p.nslabs;
+      for (int64_t tile = 0; tile < tiles; ++tile) {
+        const int slot = (int)(tile % PT_ACC_SLOTS);
+        const uint32_t acc_phase = (uint32_t)((tile / PT_ACC_SLOTS) & 1);
+        const int sl = (int)(tile % p.nslabs);
+        const int kc_begin = sl * p.slab, kc_end = (kc_begin + p.slab < p.nk) ? kc_begin + p.slab : p.nk;
         mbar_wait(&acc_empty[slot], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(slot * PT_MAX_N);
-        for (int kc = 0; kc < p.nk; ++kc) {
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           const uint32_t sb = smem_u32(stage_base + stage * PT_STAGE_BYTES);
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
 #pragma unroll
           for (int ks = 0; ks < PT_KC / 8; ++ks) {  // A_hi (raw, truncated by the tensor core) x V_hi, x V_lo
             const uint64_t a = make_k_major_desc(sb + ks * 32u);
-            tcgen05_mma_tf32(tmem_d, a, make_k_major_desc(sb + 2 * PT_A_BYTES + ks * 32u), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            tcgen05_mma_tf32(tmem_d, a, make_k_major_desc(sb + 2 * PT_A_BYTES + ks * 32u), idesc, (kc > kc_begin || ks > 0) ? 1u : 0u);
             tcgen05_mma_tf32(tmem_d, a, make_k_major_desc(sb + 2 * PT_A_BYTES + PT_B_BYTES + ks * 32u), idesc, 1u);
           }
           mbar_wait(&split_bar[stage], phase);  // A_lo written and fenced
@@ -182,9 +189,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ================= epilogue warps =================
     const int lane_group = warp_idx & 3;
     const int row_in_tile = lane_group * 32 + lane;
-    for (int64_t blk = 0; blk < my_blocks; ++blk) {
-      const int slot = (int)(blk % PT_ACC_SLOTS);
-      const uint32_t acc_phase = (uint32_t)((blk / PT_ACC_SLOTS) & 1);
+    const int64_t tiles = my_blocks * p.nslabs;
+    for (int64_t tile = 0; tile < tiles; ++tile) {
+      const int slot = (int)(tile % PT_ACC_SLOTS);
+      const uint32_t acc_phase = (uint32_t)((tile / PT_ACC_SLOTS) & 1);
+      const int64_t blk = tile / p.nslabs;
+      const bool add = (tile % p.nslabs) != 0;  // later slabs of a row block add to what this warp stored before
       const int64_t rb = blockIdx.x + blk * (int64_t)gridDim.x;
       const int64_t grow = rb * PT_BM + row_in_tile;
       mbar_wait(&acc_full[slot], acc_phase);
@@ -198,14 +208,20 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if ((p.r & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              if (c0 + 4 * q + 3 < p.r)
-                __stcs(reinterpret_cast<float4*>(out + 4 * q),
-                       make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                   __uint_as_float(v[4 * q + 3])));
+              if (c0 + 4 * q + 3 < p.r) {
+                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                float4* dst = reinterpret_cast<float4*>(out + 4 * q);
+                if (add) {
+                  const float4 old = *dst;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *dst = o;
+              }
           } else {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (c0 + q < p.r) out[q] = __uint_as_float(v[q]);
+              if (c0 + q < p.r) out[q] = add ? out[q] + __uint_as_float(v[q]) : __uint_as_float(v[q]);
           }
         }
       }
@@ -270,6 +286,8 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   p.rows = rows; p.K = (int)K; p.r = r; p.npad = (r + 15) / 16 * 16;
   p.num_row_blocks = (rows + PT_BM - 1) / PT_BM;
   p.nk = (int)((K + PT_KC - 1) / PT_KC);
+  p.slab = PT_SLAB_CHUNKS;
+  p.nslabs = (p.nk + p.slab - 1) / p.slab;
   p.C = C;
   float* Vhi = static_cast<float*>(ws);
   float* Vlo = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)p.npad * K * sizeof(float)));
