@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("shape", [(8192, 128), (10000, 64), (4096, 256), (5000, 320), (3001, 100), (2048, 2048), (70000, 32),
-                                   (16384, 512)])
+                                   (16384, 512), (3000, 640), (5000, 1000)])
 def test_gram_tc_matches_fp64(shape):
     from tntorch_b200 import ops
 
@@ -32,7 +32,13 @@ def test_gram_tc_structured_exact():
     that random data would hide behind the tolerance)."""
     from tntorch_b200 import ops
 
-    rows, n = 4096 + 37, 384
+    for rows, n in ((4096 + 37, 384), (2048 + 5, 1024), (1000, 768)):
+        _exact_case(rows, n)
+
+
+def _exact_case(rows, n):
+    from tntorch_b200 import ops
+
     i = torch.arange(rows, dtype=torch.float64)[:, None]
     j = torch.arange(n, dtype=torch.float64)[None, :]
     A = (((i * 7 + j * 13) % 17) - 8).float().cuda()  # small integers

@@ -18,6 +18,7 @@
 #include "jacobi.cuh"
 #include "small_kernels.cuh"
 #include "gram_tc.cuh"
+#include "gram_tc2.cuh"
 #include "project.cuh"
 #include "project_tc.cuh"
 
@@ -39,6 +40,11 @@ inline int project_any(const T* A, int64_t rows, int64_t n, const T* V, int64_t 
     return project_f32_fast(reinterpret_cast<const float*>(A), rows, n, reinterpret_cast<const float*>(V), (int)r,
                             reinterpret_cast<float*>(C), st);
   return gemm_direct<T, T, T, T>(rows, r, n, A, n, true, V, r, false, C, r, (T)1, nullptr, 0, (T)0, nullptr, 0, (T)0, st);
+}
+
+inline bool gram_use_pairs(int64_t rows, int64_t n) {
+  static const bool disabled = getenv("TNB_GRAM_TC2") && atoi(getenv("TNB_GRAM_TC2")) == 0;  // A/B switch for profiling
+  return !disabled && gram_tc2_shape_ok(rows, n);
 }
 
 constexpr int64_t TC_MIN_ROWS = 2048;  // below this the generic fp64-accumulating Gram is used
@@ -103,7 +109,7 @@ inline void gram_carve(ArenaT& ar, int64_t rows, int64_t n, bool allow_tc, GramW
   w.tc_bytes = 0;
   w.tc_ws = nullptr;
   if (allow_tc && std::is_same<T, float>::value && tall && rows >= TC_MIN_ROWS && gram_tc_shape_ok(rows, n)) {
-    w.tc_bytes = gram_tc_workspace_bytes(rows, n);
+    w.tc_bytes = std::max(gram_tc_workspace_bytes(rows, n), gram_tc2_shape_ok(rows, n) ? gram_tc2_workspace_bytes(rows, n) : 0);
     w.tc_ws = ar.template take<char>(w.tc_bytes);
   }
 }
@@ -116,6 +122,8 @@ inline int gram_small_side(const T* C, int64_t rows, int64_t n, double* G, float
   if (tall) {
     if (use_tc && w.tc_ws && std::is_same<T, float>::value) {
       if (used_tc) *used_tc = 1;
+      if (gram_use_pairs(rows, n))  // wide Gram: 256 x 256 tiles on CTA pairs
+        return gram_tc2_f32(reinterpret_cast<const float*>(C), rows, n, G, Gf, w.tc_ws, w.tc_bytes, st);
       return gram_tc_f32(reinterpret_cast<const float*>(C), rows, n, G, Gf, w.tc_ws, w.tc_bytes, st);
     }
     GemmPlan pl = plan_gemm(n, n, rows, true);

@@ -6,6 +6,7 @@
 #include "small_kernels.cuh"
 #include "eig.cuh"
 #include "gram_tc.cuh"
+#include "gram_tc2.cuh"
 #include "sweep.cuh"
 #include "round_impl.cuh"
 #include "cp_als.cuh"
@@ -297,13 +298,16 @@ int tnb_gram(int dtype, const void* A, int64_t rows, int64_t n, double* G, void*
 
 size_t tnb_gram_tc_workspace_bytes(int64_t rows, int64_t n) {
   if (!gram_tc_shape_ok(rows, n)) return 0;
-  return gram_tc_workspace_bytes(rows, n) + 256;
+  size_t b = gram_tc_workspace_bytes(rows, n);
+  if (gram_tc2_shape_ok(rows, n)) b = std::max(b, gram_tc2_workspace_bytes(rows, n));
+  return b + 256;
 }
 
 int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* workspace, size_t workspace_bytes,
                     void* stream) {
   TNB_TRY(require_device());
   if (!A || !G || !workspace) return fail(TNB_ERR_INVALID, "tnb_gram_tc_f32: null argument");
+  if (gram_use_pairs(rows, n)) return gram_tc2_f32(A, rows, n, G, nullptr, workspace, workspace_bytes, as_stream(stream));
   return gram_tc_f32(A, rows, n, G, nullptr, workspace, workspace_bytes, as_stream(stream));
 }
 
