@@ -34,7 +34,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="generic CUDA-core kernels only (A/B runs)")
     ap.add_argument("--cpu-shape", default="32,32,32,32,32", help="bounded sample timed on the host cores")
-    ap.add_argument("--per-gpu-batch", type=int, default=2,
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (-1: 8 when per-gpu-batch > 1)")
+    ap.add_argument("--per-gpu-batch", type=int, default=4,
                     help="independent tensors decomposed concurrently per GPU (one CUDA stream + host thread each): the "
                          "latency-bound eigen phases of one overlap the bandwidth-bound Gram/projection phases of another")
     return ap.parse_args()
@@ -213,6 +214,8 @@ def run_ours(args):
     bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
 
     PB = max(1, args.per_gpu_batch)
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (8 if PB > 1 else 0)
+    ops.set_reserved_sms(reserve)
     Xs, plans, streams = [], [], []
     for b in range(PB):
         g = torch.Generator(device=dev).manual_seed(1234 + rank_id * 16 + b)
@@ -394,7 +397,7 @@ def run_ours(args):
             if not args.no_tc else "f32 (fp64-accumulated Gram, fp32 projections)",
             "data": "synthetic",
             "config": {"workload": f"TT-SVD randn{list(shape)} fp32 -> TT-rank {args.rank} (stand-in for the infeasible 64^8: 1.1 PB)",
-                       "per_gpu_batch": PB, "in_flight_per_gpu": PB,
+                       "per_gpu_batch": PB, "in_flight_per_gpu": PB, "reserved_sms": reserve,
                        "parallelism": f"batch-sharded x{world} ({PB} independent tensors in flight per GPU on {PB} streams), all-gather of final cores",
                        "l2": "input 4 GiB >> 126 MB L2 (no flush needed)", "ranks": ranks},
             "rel_error": relerr,

@@ -46,6 +46,9 @@ int tnb_version(void);
 const char* tnb_last_error(void);
 /* number of kernel launches issued by this library since process start (bench.py `gpu_launches`) */
 uint64_t tnb_launch_count(void);
+/* Number of SMs the one-CTA-per-SM kernels (tensor-core Gram, projection) leave free, so that the latency-bound
+ * one-CTA kernels of another in-flight decomposition (other stream) can run beside them.  Default 0. */
+void tnb_set_reserved_sms(int32_t n);
 /* 1 if the tcgen05/TMA kernels are usable on the current device (sm_100), else 0 */
 int tnb_has_tensorcore_path(void);
 

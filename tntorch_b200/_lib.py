@@ -37,6 +37,7 @@ SIGNATURES = {
     "tnb_last_error": (C.c_char_p, []),
     "tnb_launch_count": (C.c_uint64, []),
     "tnb_has_tensorcore_path": (C.c_int, []),
+    "tnb_set_reserved_sms": (None, [C.c_int32]),
     "tnb_ttsvd_cores_capacity": (C.c_int64, [C.c_int, _i64p, _i32p, _i64p]),
     "tnb_ttsvd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, _i32p, C.c_uint32]),
     "tnb_ttsvd": (C.c_int, [C.c_int, _vp, C.c_int, _i64p, _i32p, C.c_double, C.c_uint32, _vp, C.c_size_t, _vp,

@@ -118,6 +118,21 @@ inline const DeviceInfo& device_info() {
   return info;
 }
 
+// SMs left free by the persistent / one-CTA-per-SM kernels (tensor-core Gram, projection).  With several
+// decompositions in flight on different streams the latency-bound one-CTA kernels of one tensor (Jacobi, Cholesky,
+// rank rule) then run beside the bandwidth-bound kernels of another instead of queueing behind them.
+inline std::atomic<int>& reserved_sms_ref() {
+  static std::atomic<int> r{0};
+  return r;
+}
+inline int usable_sms() {
+  const int sms = device_info().valid ? device_info().sm_count : 148;
+  int r = reserved_sms_ref().load(std::memory_order_relaxed);
+  if (r < 0) r = 0;
+  if (r > sms - 8) r = sms - 8;
+  return sms - r;
+}
+
 // Pinned host scratch for reading small results back (ranks, Ritz values).
 inline void* pinned_scratch(size_t bytes) {
   static thread_local void* p = nullptr;

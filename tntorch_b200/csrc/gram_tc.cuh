@@ -374,7 +374,7 @@ inline void gram_tc_plan(int64_t rows, int64_t n, GramTcParams& p, int64_t m_col
   }
   p.num_tiles = cnt;
   p.iters_total = (rows + TC_KC - 1) / TC_KC;
-  int sms = device_info().valid ? device_info().sm_count : 148;
+  int sms = usable_sms();
   int64_t ks = sms / cnt;
   if (ks < 1) ks = 1;
   if (ks > p.iters_total) ks = p.iters_total;

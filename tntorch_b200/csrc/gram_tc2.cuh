@@ -208,7 +208,7 @@ inline void gram_tc2_plan(int64_t rows, int64_t n, GramTc2Params& p) {
   p.nb = (int)((n + 255) / 256);
   p.num_tiles = p.nb * (p.nb + 1) / 2;
   p.iters_total = (rows + TC_KC - 1) / TC_KC;
-  const int sms = device_info().valid ? device_info().sm_count : 148;
+  const int sms = usable_sms();
   int64_t ks = (sms / 2) / p.num_tiles;
   if (ks < 1) ks = 1;
   if (ks > p.iters_total) ks = p.iters_total;

@@ -126,7 +126,7 @@ inline int project_f32_fast(const float* A, int64_t rows, int64_t n, const float
   const int tx = r <= 32 ? 8 : 16;  // 128 x 32 or 64 x 64 output tile (static shared memory stays below 48 KB)
   const int br = (256 / tx) * 4;
   int64_t blocks = ceil_div<int64_t>(rows, br);
-  const int sms = device_info().valid ? device_info().sm_count : 148;
+  const int sms = usable_sms();
   if (blocks > (int64_t)sms * 3) blocks = (int64_t)sms * 3;  // persistent: 3 resident CTAs per SM loop over the row blocks
   if (tx == 8)
     project_f32_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(A, rows, (int)n, V, r, C);

@@ -302,7 +302,7 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
     TNB_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
     attr_set = true;
   }
-  const int sms = device_info().valid ? device_info().sm_count : 148;
+  const int sms = usable_sms();
   const int64_t grid = p.num_row_blocks < sms ? p.num_row_blocks : sms;
   project_tc_kernel<<<(unsigned)grid, PT_THREADS, PT_SMEM_BYTES, st>>>(ta, th, tl, p);
   TNB_LAUNCH_CHECK();

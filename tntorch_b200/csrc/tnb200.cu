@@ -39,6 +39,7 @@ int tnb_version(void) { return 100; }
 const char* tnb_last_error(void) { return last_error_ref().c_str(); }
 uint64_t tnb_launch_count(void) { return launch_counter().load(); }
 int tnb_has_tensorcore_path(void) { return tc_path_available() ? 1 : 0; }
+void tnb_set_reserved_sms(int32_t n) { reserved_sms_ref().store(n); }
 
 // ------------------------------------------------------------------ dense TT-SVD
 int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host) {

@@ -59,6 +59,11 @@ def launch_count() -> int:
     return int(lib().tnb_launch_count())
 
 
+def set_reserved_sms(n: int) -> None:
+    """Leave n SMs free in the persistent kernels (useful with several decompositions in flight on different streams)."""
+    lib().tnb_set_reserved_sms(int(n))
+
+
 def has_tensorcore_path() -> bool:
     return bool(lib().tnb_has_tensorcore_path())
 
