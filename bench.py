@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="generic CUDA-core kernels only (A/B runs)")
     ap.add_argument("--cpu-shape", default="32,32,32,32,32", help="bounded sample timed on the host cores")
-    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (-1: 8 when per-gpu-batch > 1)")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (measured: no gain on B200, default 0)")
     ap.add_argument("--per-gpu-batch", type=int, default=4,
                     help="independent tensors decomposed concurrently per GPU (one CUDA stream + host thread each): the "
                          "latency-bound eigen phases of one overlap the bandwidth-bound Gram/projection phases of another")
@@ -214,7 +214,7 @@ def run_ours(args):
     bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
 
     PB = max(1, args.per_gpu_batch)
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else (8 if PB > 1 else 0)
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else 0
     ops.set_reserved_sms(reserve)
     Xs, plans, streams = [], [], []
     for b in range(PB):
