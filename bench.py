@@ -308,8 +308,8 @@ def run_ours(args):
     # the Gram and projection phases are ONE kernel each (gram_tc_kernel / project_f32_kernel); the eigen phases are
     # chains of ~100 small launches and are reported as a share instead (phases_ms.eig_ms)
     for s in range(nsteps):
-        cand.append((phase["gram_ms"][s], f"gram_tc_kernel (Gram of step {s})", s, "gram"))
-        cand.append((phase["factor_ms"][s], f"project_f32_kernel (projection of step {s})", s, "factor"))
+        cand.append((phase["gram_ms"][s], f"Gram of step {s}", s, "gram"))
+        cand.append((phase["factor_ms"][s], f"project_tc_kernel (3xTF32 projection of step {s})", s, "factor"))
     cand.sort(reverse=True)
     top_ms, top_name, top_s, top_kind = cand[0]
     # algorithmic work of that phase
@@ -325,11 +325,12 @@ def run_ours(args):
     rws, cls, rr = dims[top_s]
     if top_kind == "gram":
         if cls <= 512:  # narrow Gram: HBM-bound, one read of the carry
-            roof = {"kernel": top_name, "bound": "hbm", "achieved": rws * cls * 4 / top_ms / 1e6, "peak": hbm_peak,
-                    "unit": "GB/s", "alg_bytes": rws * cls * 4}
+            roof = {"kernel": "gram_tc_kernel (" + top_name + ")", "bound": "hbm", "achieved": rws * cls * 4 / top_ms / 1e6,
+                    "peak": hbm_peak, "unit": "GB/s", "alg_bytes": rws * cls * 4}
         else:  # compute-bound symmetric Gram: rows*cols^2 MACs on the upper triangle -> rows*cols*(cols+1) flops
             fl = rws * cls * (cls + 1)
-            roof = {"kernel": top_name, "bound": "tensor", "achieved": fl / top_ms / 1e9, "peak": bf16_sus / 2,
+            roof = {"kernel": "gram_tc2_kernel, cta_group::2 (" + top_name + ")", "bound": "tensor",
+                    "achieved": fl / top_ms / 1e9, "peak": bf16_sus / 2,
                     "unit": "TFLOP/s", "alg_flops": fl,
                     "peak_note": "TF32 dense peak taken as half the measured sustained bf16 cuBLAS rate (no TF32 entry in MEASURED_PEAKS.json)"}
     elif top_kind == "factor":
@@ -341,7 +342,13 @@ def run_ours(args):
         roof = {"kernel": top_name, "bound": "hbm", "achieved": by / top_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                 "alg_bytes": by, "note": "latency-bound subspace eigensolver (dependent chain of small GEMMs)"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_summaries.md) for the default 64^5 / r=32 workload; null for other shapes
     roof["traffic"] = None
+    if list(shape) == [64] * 5 and args.rank == 32 and not args.no_tc:
+        ncu_traffic = {("gram", 0): 4.295e9 + 0.004e9, ("factor", 0): 4.297e9 + 2.15e9, ("gram", 1): 4.937e9 + 0.02e9}
+        roof["traffic"] = ncu_traffic.get((top_kind, top_s))
+        roof["traffic_source"] = "profiles/r01_ncu_summaries.md (ncu --set full, per launch)"
     roof["ms"] = top_ms
     roof["peak_source"] = peak_src
     sweep_roof = {"alg_bytes_per_tensor": B_alg, "achieved_GBps": PB * B_alg / ms_step / 1e6, "peak_GBps": hbm_peak,
@@ -354,28 +361,53 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         del prof_plan
-        hplan = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, host_io=True)
-        hplan.ws = plan.ws
-        hplan.cores_buf = plan.cores_buf
-        Xh = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-        Xh.copy_(X)
+        # two host-buffer pipelines per GPU: the H2D copy of one tensor overlaps the kernels of the other (the PCIe
+        # link is the bound: 4 GiB per tensor); every step still moves its own input and its own result
+        EB = 2 if PB > 1 else 1
+        hplans, Xhs = [], []
+        for b in range(EB):
+            hp = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, host_io=True)
+            hp.ws = plans[b % PB].ws
+            hp.cores_buf = plans[b % PB].cores_buf
+            hplans.append(hp)
+            xh = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            xh.copy_(Xs[b % PB])
+            Xhs.append(xh)
+
+        def run_host_one(b):
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(streams[b]):
+                hc = hplans[b].run_host(Xhs[b])
+                return float(hc[0][0, 0, 0])  # the result is on the host
+
+        def e2e_step():
+            if EB == 1:
+                return [run_host_one(0)]
+            cur = torch.cuda.current_stream()
+            for sb in streams[:EB]:
+                sb.wait_stream(cur)
+            r = list(pool.map(run_host_one, range(EB)))
+            for sb in streams[:EB]:
+                cur.wait_stream(sb)
+            return r
+
         for _ in range(2):
-            hplan.run_host(Xh)
+            e2e_step()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         ksteps = max(2, min(args.steps, 5))
         for _ in range(ksteps):
-            hc = hplan.run_host(Xh)
-            _ = float(hc[0][0, 0, 0])  # the result is on the host
+            e2e_step()
         f1.record()
         barrier()
         tt = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ems = float(tt.item()) / ksteps
-        e2e = {"value": world * numel / (ems * 1e-3) / 1e9, "unit": "GElements/s", "ms_per_step": ems,
-               "h2d_bytes_per_step": numel * 4, "d2h_bytes_per_step": int(hplan.cap) * 4, "steps": ksteps}
+        e2e = {"value": world * EB * numel / (ems * 1e-3) / 1e9, "unit": "GElements/s", "ms_per_step": ems,
+               "h2d_bytes_per_step": EB * numel * 4, "d2h_bytes_per_step": EB * int(hplans[0].cap) * 4, "steps": ksteps,
+               "tensors_per_step": EB}
 
     cpu = None
     if rank_id == 0 and not args.no_cpu_baseline:
@@ -393,7 +425,7 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": "GElements/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (Gram on tcgen05 kind::tf32 with fp32 TMEM accumulation; projections fp32 FFMA; eigen fp32/fp64)"
+            "vs_baseline": None, "dtype": "f32 (Gram: tcgen05 kind::tf32, fp32 TMEM accumulation; projections: 3xTF32 on tcgen05 = fp32 accuracy; Gram matrices, eigenproblems and rank rule in fp64)"
             if not args.no_tc else "f32 (fp64-accumulated Gram, fp32 projections)",
             "data": "synthetic",
             "config": {"workload": f"TT-SVD randn{list(shape)} fp32 -> TT-rank {args.rank} (stand-in for the infeasible 64^8: 1.1 PB)",

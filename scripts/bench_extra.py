@@ -1,0 +1,54 @@
+"""Timings of the other BASELINE.json configs (informational; the driver's headline is bench.py).
+   python scripts/bench_extra.py [cfg3] [cfg4] [cfg5]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import tntorch_b200 as tnb
+from tntorch_b200 import ops
+
+def ev_ms(fn, n=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return min(ts)
+
+which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
+out = {}
+if "cfg3" in which:  # tn.round_tt on random TT 128^10 rank 64 -> 16, fp64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rs = [1] + [64] * 9 + [1]
+    cores = [torch.randn(rs[k], 128, rs[k + 1], generator=g, device="cuda", dtype=torch.float64) for k in range(10)]
+    t = tnb.Tensor(cores)
+    ms = ev_ms(lambda: tnb.round_tt(t, rmax=16), n=3)
+    t2 = tnb.round_tt(t, rmax=16)
+    coef = sum(c.numel() for c in cores)
+    out["cfg3_round_tt_128^10_r64to16_f64"] = {"ms": ms, "Mcoef_per_s": coef / ms / 1e3, "ranks": t2.ranks_tt.tolist()}
+    print(json.dumps(out), flush=True)
+if "cfg4" in which:  # CP-ALS R=50 on a synthetic rank-50 256^4 (16 GiB fp32); a few sweeps timed, per-sweep reported
+    shape = (256,) * 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    fs = [torch.randn(s, 50, generator=g, device="cuda") for s in shape]
+    X = torch.einsum("ar,br,cr,dr->abcd", *fs)
+    X += 1e-2 * X.std() * torch.randn(shape, generator=g, device="cuda")
+    del fs
+    torch.cuda.synchronize(); t0 = time.time()
+    fac, info = ops.cp_als(X, 50, max_iter=5, tol=float("-inf"), return_info=True)
+    torch.cuda.synchronize(); dt = time.time() - t0
+    t1 = time.time(); fac2, info2 = ops.cp_als(X, 50, max_iter=1, tol=float("-inf"), return_info=True); torch.cuda.synchronize(); d1 = time.time() - t1
+    out["cfg4_cp_als_256^4_R50_f32"] = {"s_per_sweep": (dt - d1) / 4, "init_plus_1_sweep_s": d1, "errors": info["errors"]}
+    print(json.dumps(out), flush=True)
+    del X
+if "cfg5" in which:  # TT-cross 32^6, ranks 10, 3 sweeps (the unit of BASELINE configs[4]); sequential problems
+    dom = [torch.linspace(0, 1, 32, dtype=torch.float64) for _ in range(6)]
+    np.random.seed(0); torch.manual_seed(0)
+    nprob = 4
+    torch.cuda.synchronize(); t0 = time.time()
+    for b in range(nprob):
+        sh = 1.0 + b / 512.0
+        t, info = tnb.cross(lambda *xs: 1.0 / (sh + sum(xs)), domain=dom, ranks_tt=10, max_iter=3, verbose=False,
+                            return_info=True, suppress_warnings=True)
+    torch.cuda.synchronize(); dt = (time.time() - t0) / nprob
+    out["cfg5_cross_32^6_r10_3sweeps_f64"] = {"s_per_problem": dt, "evals_per_s": info["nsamples"] / dt, "val_eps": float(info["val_eps"])}
+    print(json.dumps(out), flush=True)
