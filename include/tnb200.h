@@ -134,6 +134,10 @@ size_t tnb_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r);
 int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t max_iters, void* workspace,
                size_t workspace_bytes, int32_t* index_dev, double* C_dev, int32_t* iters_host, void* stream);
 
+/* C (M x N) = A (M x K) B (K x N), all row-major, same dtype (fp32: fp32 accumulate; fp64: fp64), CUDA-core tiles.
+ * Replaces: `R @ right_unfolding(next)` tensor.py:1826-1832 and `leftcoreL @ L` tensor.py:1868-1878. */
+int tnb_matmul(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, void* stream);
+
 /* Tall-skinny Householder QR of `nbatch` fp64 matrices (rows x n, row-major): Q (rows x min(rows,n)) explicit,
  * optional R (min(rows,n) x n).  Warp-shuffle reflector kernels, one CTA per matrix.
  * Replaces: torch.linalg.qr(V) before maxvol in tn.cross (cross.py:398, 430) and the QR of

@@ -50,3 +50,29 @@ def test_truncated_svd_matches_reference(name, lo):
         eye = torch.eye(r, device="cuda", dtype=left.dtype)
         orth = (left.T @ left - eye) if lo else (right @ right.T - eye)
         assert orth.abs().max().item() < (1e-4 if M.dtype == np.float32 else 1e-8)
+
+
+def test_orthogonalization_preserves_tensor():
+    """tests/test_round.py:7-18: left_/right_/orthogonalize leave the tensor unchanged (<= 1e-7) and produce
+    orthonormal unfoldings."""
+    import tntorch_b200 as tnb
+
+    cores = cases.random_tt((6, 5, 7, 4, 6), 5, seed=77)
+    gt = cases.tt_full(cores)
+    t = tnb.Tensor([torch.as_tensor(c).cuda() for c in cores])
+    R = t.left_orthogonalize(1)
+    assert R.shape[0] == t.cores[1].shape[-1]
+    assert relerr64(gt, t.cores) <= 1e-7
+    L = t.right_orthogonalize(3)
+    assert L.shape[1] == t.cores[3].shape[0]
+    assert relerr64(gt, t.cores) <= 1e-7
+    t.orthogonalize(2)
+    assert relerr64(gt, t.cores) <= 1e-7
+    for k in (0, 1):
+        M = t.cores[k].reshape(-1, t.cores[k].shape[-1])
+        assert (M.T @ M - torch.eye(M.shape[1], device="cuda", dtype=M.dtype)).abs().max().item() < 1e-10
+    for k in (3, 4):
+        M = t.cores[k].reshape(t.cores[k].shape[0], -1)
+        assert (M @ M.T - torch.eye(M.shape[0], device="cuda", dtype=M.dtype)).abs().max().item() < 1e-10
+    with pytest.raises(AssertionError):
+        t.left_orthogonalize(4)

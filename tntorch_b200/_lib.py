@@ -57,6 +57,7 @@ SIGNATURES = {
                              _f64p, _i32p, _vp]),
     "tnb_maxvol_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_maxvol": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp, C.c_size_t, _vp, _vp, _i32p, _vp]),
+    "tnb_matmul": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "tnb_qr_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_qr_householder": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),
     "tnb_gram_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64]),

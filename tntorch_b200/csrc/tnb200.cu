@@ -260,6 +260,19 @@ int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol
                     as_stream(stream));
 }
 
+int tnb_matmul(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1) return fail(TNB_ERR_INVALID, "tnb_matmul: bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == TNB_F32)
+    return gemm_direct<float, float, float, float>(M, N, K, static_cast<const float*>(A), K, true, static_cast<const float*>(B),
+                                                   N, false, static_cast<float*>(C), N, 1.f, nullptr, 0, 0.f, nullptr, 0, 0.f, st);
+  return gemm_direct<double, double, double, double>(M, N, K, static_cast<const double*>(A), K, true,
+                                                     static_cast<const double*>(B), N, false, static_cast<double*>(C), N, 1.0,
+                                                     nullptr, 0, 0.0, nullptr, 0, 0.0, st);
+}
+
 size_t tnb_qr_workspace_bytes(int32_t nbatch, int32_t rows, int32_t n) {
   if (nbatch < 1 || rows < 1 || n < 1) return 0;
   return householder_qr_workspace_bytes(nbatch, rows, n) + 256;

@@ -291,6 +291,19 @@ def maxvol(A: torch.Tensor, tol: float = 1.05, max_iters: int = 100, return_iter
     return index, Cm
 
 
+def matmul(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """Row-major A @ B on the library's own GEMM (no cuBLAS)."""
+    _require_cuda(A, "matmul")
+    A, B = A.contiguous(), B.contiguous()
+    assert A.dtype == B.dtype and A.shape[1] == B.shape[0]
+    M, K = A.shape
+    N = B.shape[1]
+    Cm = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().tnb_matmul(_dtype_code(A), _ptr(A), _ptr(B), _ptr(Cm), M, N, K, _stream()))
+    return Cm
+
+
 def qr(A: torch.Tensor, return_r: bool = False):
     """Householder QR on the device (torch.linalg.qr semantics, reduced): A [rows, n] or batch [B, rows, n], fp64."""
     _require_cuda(A, "qr")

@@ -157,6 +157,49 @@ class Tensor(object):
     def numpy(self):
         return self.torch().detach().cpu().numpy()
 
+    # ------------------------------------------------------------------ orthogonalisation (tensor.py:1800-1909)
+    def left_orthogonalize(self, mu: int):
+        """Makes the mu-th core left-orthogonal and pushes the R factor to its right core; returns R
+        (tensor.py:1800-1833).  Householder QR and the R push run in libtnb200 (tnb_qr_householder, tnb_matmul)."""
+        assert 0 <= mu < self.dim() - 1
+        if self.batch:
+            raise NotImplementedError("batched orthogonalisation is not built")
+        c = self.cores[mu]
+        Q, R = ops.qr(c.reshape(-1, c.shape[-1]), return_r=True)
+        Q, R = Q.to(c.dtype), R.to(c.dtype)
+        self.cores[mu] = Q.reshape(c.shape[:-1] + (Q.shape[1],))
+        nxt = self.cores[mu + 1]
+        self.cores[mu + 1] = ops.matmul(R, nxt.reshape(nxt.shape[0], -1)).reshape((R.shape[0],) + nxt.shape[1:])
+        return R
+
+    def right_orthogonalize(self, mu: int):
+        """Makes the mu-th core right-orthogonal and pushes the L factor to its left core; returns L
+        (tensor.py:1835-1879)."""
+        assert 1 <= mu < self.dim()
+        if self.batch:
+            raise NotImplementedError("batched orthogonalisation is not built")
+        c = self.cores[mu]
+        Q, L = ops.qr(c.reshape(c.shape[0], -1).t().contiguous(), return_r=True)
+        L, Q = L.t().contiguous().to(c.dtype), Q.t().contiguous().to(c.dtype)
+        self.cores[mu] = Q.reshape((Q.shape[0],) + c.shape[1:])
+        prv = self.cores[mu - 1]
+        self.cores[mu - 1] = ops.matmul(prv.reshape(-1, prv.shape[-1]), L).reshape(prv.shape[:-1] + (L.shape[1],))
+        return L
+
+    def orthogonalize(self, mu: int):
+        """All left and right orthogonalisations needed to make the tensor mu-orthogonal; returns (R, L)
+        (tensor.py:1881-1909)."""
+        if mu < 0:
+            mu += self.dim()
+        dt, dev = self.cores[0].dtype, self.cores[0].device
+        R = torch.ones(1, 1, dtype=dt, device=dev)
+        L = torch.ones(1, 1, dtype=dt, device=dev)
+        for i in range(mu):
+            R = self.left_orthogonalize(i)
+        for i in range(self.dim() - 1, mu, -1):
+            L = self.right_orthogonalize(i)
+        return R, L
+
     # ------------------------------------------------------------------ rounding (tensor.py:2008-2098)
     def round_tt(self, eps: float = 1e-14, rmax=None, algorithm: Optional[str] = "svd", verbose: Optional[bool] = False):
         """In place, by rebinding ``self.cores`` (same contract as the reference)."""
