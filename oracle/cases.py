@@ -187,3 +187,14 @@ def cross_function(shift):
         return 1.0 / s
 
     return f
+
+# ---- Tucker rounding / tn.round / Tensor(eps=) ---------------------------------------------
+TUCKER_CASES = {
+    "dense_randn16x3_tucker3": dict(kind="dense", spec=dict(kind="randn", shape=(16, 16, 16), seed=70, dtype="float64"), ranks_tucker=3),
+    "dense_analytic128_tucker3": dict(kind="dense", spec=dict(kind="analytic128", dtype="float64"), ranks_tucker=3),
+    "dense_analytic128_eps": dict(kind="dense", spec=dict(kind="analytic128", dtype="float64"), eps=1e-5),
+    "dense_twin_eps": dict(kind="dense", spec=dict(kind="tt_noise", shape=(12, 10, 8, 9, 7), rank=4, noise=1e-6, seed=7, dtype="float64"), eps=1e-4),
+    "tt_round_tucker_eps": dict(kind="tt", spec=dict(shape=(16,) * 4, rank=6, seed=71, dtype="float64"), round_tucker=dict(eps=0.2)),
+    "tt_round_tucker_rmax": dict(kind="tt", spec=dict(shape=(12, 14, 10, 9), rank=5, seed=72, dtype="float64"), round_tucker=dict(rmax=4)),
+    "tt_round_eps": dict(kind="tt", spec=dict(shape=(10,) * 5, rank=7, seed=24, dtype="float64"), round=dict(eps=0.3)),
+}

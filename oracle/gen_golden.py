@@ -122,6 +122,31 @@ def gen_cpals():
     np.savez_compressed(os.path.join(OUT, "cp_als.npz"), **out)
 
 
+def gen_tucker():
+    out = {}
+    torch.set_default_dtype(torch.float64)
+    for name, c in cases.TUCKER_CASES.items():
+        if c["kind"] == "dense":
+            X = cases.make_dense(c["spec"])
+            kw = {k: c[k] for k in ("ranks_tucker", "eps") if k in c}
+            t = tn.Tensor(torch.as_tensor(X), **kw)
+            dense = X
+        else:
+            cores = cases.make_tt(c["spec"])
+            dense = cases.tt_full(cores)
+            t = tn.Tensor([torch.as_tensor(x.copy()) for x in cores])
+            if "round_tucker" in c:
+                t.round_tucker(**c["round_tucker"])
+            else:
+                t.round(**c["round"])
+        out[f"{name}/ranks_tt"] = np.asarray(t.ranks_tt, dtype=np.int64)
+        out[f"{name}/ranks_tucker"] = np.asarray(t.ranks_tucker, dtype=np.int64)
+        out[f"{name}/relerr"] = np.float64(rel_err64(dense, t))
+        print(name, list(t.ranks_tt), list(t.ranks_tucker), out[f"{name}/relerr"], flush=True)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "tucker.npz"), **out)
+
+
 def gen_cross():
     out = {}
     torch.set_default_dtype(torch.float64)
@@ -148,7 +173,7 @@ def gen_cross():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross"]
+    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross", "tucker"]
     if "ttsvd" in which:
         gen_ttsvd()
     if "round" in which:
@@ -161,3 +186,5 @@ if __name__ == "__main__":
         gen_cpals()
     if "cross" in which:
         gen_cross()
+    if "tucker" in which:
+        gen_tucker()

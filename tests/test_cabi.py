@@ -74,4 +74,4 @@ def test_reference_error_behaviour_at_the_boundary():
     with pytest.raises(ValueError):  # round.py:77-78
         tnb.truncated_svd(torch.zeros(3, 3), delta=1.0, eps=1.0)
     with pytest.raises(NotImplementedError):
-        tnb.Tensor(torch.zeros(3, 3), ranks_tucker=2)
+        tnb.Tensor(torch.zeros(3, 3), ranks_cp=2, ranks_tucker=2)

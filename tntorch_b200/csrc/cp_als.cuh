@@ -128,7 +128,8 @@ inline int make_cp_dims(int ndim, const int64_t* shape, int R, CpDims& d) {
 
 // MTTKRP for mode n into Mout (I_n x R).  Y0/Y1: ping-pong buffers of numel/min(I_0,I_{N-1}) * R elements.
 template <typename T>
-inline int cp_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, T* Y0, T* Y1, T* Mout, cudaStream_t st) {
+inline int cp_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, T* Y0, T* Y1, T* Mout, cudaStream_t st,
+                     void* tc_ws = nullptr, size_t tc_ws_bytes = 0) {
   const int N = d.N;
   T* cur = Y0;
   T* nxt = Y1;
@@ -136,7 +137,7 @@ inline int cp_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, T* 
   if (n != N - 1) {
     // contract the last mode:  cur[(i_0..i_{N-2}), r] = sum_i X[.., i] A_{N-1}[i, r]
     const int64_t rows = d.numel / d.shape[N - 1];
-    TNB_TRY(project_any<T>(X, rows, d.shape[N - 1], A[N - 1], R, cur, st));
+    TNB_TRY(project_any<T>(X, rows, d.shape[N - 1], A[N - 1], R, cur, st, tc_ws, tc_ws_bytes));  // 3xTF32 on tcgen05 when it fits
     lo = 0;
     hi = N - 2;
   } else {
@@ -193,6 +194,12 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
   double* acc = ar.template take<double>(4);
   GemmPlan plg = plan_gemm(R, R, imax, false);
   double* gpart = ar.template take<double>(plg.partial_elems + 64);
+  void* ptc_ws = nullptr;
+  size_t ptc_bytes = 0;
+  if (std::is_same<T, float>::value && R <= PT_MAX_N && d.shape[N - 1] % 4 == 0 && d.shape[N - 1] >= 32) {
+    ptc_bytes = project_tc_workspace_bytes(d.shape[N - 1], R);
+    ptc_ws = ar.template take<char>(ptc_bytes);
+  }
   // HOSVD init scratch: mode Gram (I x I) + eigen workspace, sized for the largest mode
   size_t peak = ar.off;
   for (int n = 0; n < N; ++n) {
@@ -278,7 +285,7 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
   double prev_err = 0.0;
   for (; it < max_iter; ++it) {
     for (int n = 0; n < N; ++n) {
-      TNB_TRY(cp_mttkrp<T>(X, d, n, R, A.data(), Y0, Y1, Mbuf, st));
+      TNB_TRY(cp_mttkrp<T>(X, d, n, R, A.data(), Y0, Y1, Mbuf, st, ptc_ws, ptc_bytes));
       hadamard_grams_kernel<<<grid_for(R * R), 256, 0, st>>>(gp, N, n, R, P);
       TNB_LAUNCH_CHECK();
       if (n == N - 1) {  // <X, [[A]]> needs M_{N-1} and the NEW A_{N-1}; ||[[A]]||^2 needs all new grams

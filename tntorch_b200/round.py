@@ -15,6 +15,13 @@ def round_tt(t, **kwargs):
     return t2
 
 
+def round_tucker(t, **kwargs):
+    """round.py:22-34"""
+    t2 = t.clone()
+    t2.round_tucker(**kwargs)
+    return t2
+
+
 def round(t, **kwargs):
     """round.py:37-49"""
     t2 = t.clone()
@@ -50,7 +57,9 @@ def relative_error(gt, approx):
     """metrics.py:135-151 for (dense torch tensor, Tensor)."""
     from .tensor import Tensor
 
-    if isinstance(gt, torch.Tensor) and isinstance(approx, Tensor) and not approx.batch:
+    if isinstance(gt, torch.Tensor) and isinstance(approx, Tensor) and not approx.batch and all(c.dim() == 3 for c in approx.cores):
+        if any(U is not None for U in approx.Us):
+            approx = approx.decompress_tucker_factors()
         return ops.tt_relative_error(gt.to(approx.cores[0].device), approx.cores)
     a = gt.torch() if isinstance(gt, Tensor) else gt
     b = approx.torch() if isinstance(approx, Tensor) else approx

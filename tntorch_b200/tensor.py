@@ -48,11 +48,8 @@ class Tensor(object):
     ):
         assert algorithm in ("svd", "eig")  # both map onto the same Gram/eigen kernels
         self.batch = batch
-        if ranks_tucker is not None:
-            raise NotImplementedError(
-                "tntorch_b200 covers the TT / CP decomposition and TT rounding path (SURVEY.md §8); Tucker "
-                "rounding is listed as a next row and is not built yet"
-            )
+        if ranks_tucker is not None and ranks_cp is not None:
+            raise NotImplementedError("CP on a Tucker core (tensor.py:278-302) is not built")
         if isinstance(data, (list, tuple)):  # explicit cores (tensor.py:163-192)
             min_dim, max_dim = (3, 4) if batch else (2, 3)
             if not all(min_dim <= d.dim() <= max_dim for d in data):
@@ -91,14 +88,24 @@ class Tensor(object):
                         ops.cp_als(data[b], ranks_cp, max_iter=max_iter, tol=tol) for b in range(data.shape[0])])]
                 else:
                     self.cores = ops.cp_als(data, ranks_cp, max_iter=max_iter, tol=tol)
+            elif ranks_tucker is not None or (eps is not None and not batch):
+                # tensor.py:401-408 / 436-439: exact TT first (the reference's _full_rank_tt), then round_tucker /
+                # round_tt / round on it.  The exact TT needs every Gram of the sweep to fit the direct eigensolver.
+                if batch:
+                    raise NotImplementedError("batched Tucker rounding is not built")
+                self.cores = ops.ttsvd(data, rmax=None, eps=0.0)
+                self.Us = [None] * N
+                if ranks_tucker is not None:
+                    self.round_tucker(rmax=ranks_tucker, algorithm=algorithm)
+                    if ranks_tt is not None:
+                        self.round_tt(rmax=ranks_tt, algorithm=algorithm)
+                else:
+                    self.round(eps, algorithm=algorithm)
+                Us = self.Us
             elif batch:
                 # the reference's batch mode: per-sample decomposition, rank = min(rmax, len(S)), no eps
                 per = [ops.ttsvd(data[b], rmax=ranks_tt, batch_mode=True) for b in range(data.shape[0])]
                 self.cores = [torch.stack([p[k] for p in per], dim=0) for k in range(N)]
-            elif eps is not None:
-                # Tensor(data, eps=...) -> round(eps) (tensor.py:436-439); the Tucker pass of round() is a no-op
-                # for the ranks but not built here, so only the TT budget is spent.
-                self.cores = ops.ttsvd(data, rmax=None, eps=eps)
             else:
                 self.cores = ops.ttsvd(data, rmax=ranks_tt)
         if Us is None:
@@ -117,7 +124,28 @@ class Tensor(object):
 
     @property
     def shape(self):
-        return torch.Size([c.shape[-2] for c in self.cores])
+        return torch.Size([(self.Us[n].shape[-2] if self.Us[n] is not None else c.shape[-2])
+                           for n, c in enumerate(self.cores)])
+
+    @property
+    def ranks_tucker(self):
+        return torch.tensor([c.shape[-2] for c in self.cores])
+
+    def tucker_core(self):
+        """tensor.py:1565-1574"""
+        return Tensor(self.cores, batch=self.batch).torch()
+
+    def decompress_tucker_factors(self):
+        """tensor.py:1576-1627: absorb every Tucker factor into its core (einsum 'ijk,aj->iak')."""
+        cores = []
+        for c, U in zip(self.cores, self.Us):
+            if U is None:
+                cores.append(c)
+            else:
+                r0, S, r1 = c.shape
+                m = ops.matmul(U, c.permute(1, 0, 2).reshape(S, r0 * r1))  # [I, r0*r1]
+                cores.append(m.reshape(U.shape[0], r0, r1).permute(1, 0, 2).contiguous())
+        return Tensor(cores, batch=self.batch)
 
     @property
     def ranks_tt(self):
@@ -129,7 +157,8 @@ class Tensor(object):
         return sum(c.numel() for c in self.cores)
 
     def clone(self):
-        return Tensor([c.clone() for c in self.cores], batch=self.batch)
+        return Tensor([c.clone() for c in self.cores], Us=[None if U is None else U.clone() for U in self.Us],
+                      batch=self.batch)
 
     def __repr__(self):
         return f"{self.dim()}D TT tensor (B200): shape {list(self.shape)}, TT ranks {self.ranks_tt.tolist()}"
@@ -138,6 +167,8 @@ class Tensor(object):
     def torch(self):
         if self.batch:
             return torch.stack([Tensor([c[b] for c in self.cores]).torch() for b in range(self.cores[0].shape[0])])
+        if any(U is not None for U in self.Us):
+            return self.decompress_tucker_factors().torch()
         c0 = self.cores[0]
         r0 = c0.shape[0] if c0.dim() == 3 else c0.shape[1]
         f = torch.ones(1, r0, dtype=c0.dtype, device=c0.device)
@@ -215,7 +246,53 @@ class Tensor(object):
         else:
             self.cores = ops.tt_round(self.cores, eps=eps, rmax=rmax)
 
+    def round_tucker(self, eps: float = 1e-14, rmax=None, dim="all", algorithm: Optional[str] = "svd"):
+        """tensor.py:1911-2006, composed from the device primitives: orthogonalise to the last core, then for
+        mu = N-1..0 push the core's non-orthogonality into the Tucker factor (Householder QR), split the factor with
+        truncated_svd(left_ortho=True) under the budget eps/sqrt(len(dim)), absorb the remainder into the core and
+        right-orthogonalise."""
+        assert algorithm in ("svd", "eig")
+        if self.batch:
+            raise NotImplementedError("batched Tucker rounding is not built")
+        N = self.dim()
+        if not hasattr(rmax, "__len__"):
+            rmax = [rmax] * N
+        assert len(rmax) == N
+        if dim == "all":
+            dim = range(N)
+        if not hasattr(dim, "__len__"):
+            dim = [dim] * N
+        self.orthogonalize(-1)
+        for mu in range(N - 1, -1, -1):
+            c = self.cores[mu]
+            r0, S, r1 = c.shape
+            if self.Us[mu] is None:
+                self.Us[mu] = torch.eye(S, dtype=c.dtype, device=c.device)
+            Q, R = ops.qr(c.permute(0, 2, 1).reshape(r0 * r1, S), return_r=True)  # tensor.py:1972-1979
+            Q, R = Q.to(c.dtype), R.to(c.dtype)
+            k = Q.shape[1]
+            self.Us[mu] = ops.matmul(self.Us[mu], R.t().contiguous())              # I x k
+            left, right = ops.truncated_svd(self.Us[mu], eps=eps / (len(dim) ** 0.5), rmax=rmax[mu], left_ortho=True)
+            self.Us[mu] = left                                                    # I x r
+            newc = ops.matmul(Q, right.t().contiguous())                          # (r0 r1) x r
+            self.cores[mu] = newc.reshape(r0, r1, -1).permute(0, 2, 1).contiguous()
+            if mu > 0:
+                self.right_orthogonalize(mu)
+
+    def _tt_dot(self, other):
+        """<self, other> for two TT(-Tucker) tensors (metrics.dot): small interface matrices, fp64."""
+        a, b = self.decompress_tucker_factors(), other.decompress_tucker_factors()
+        f = torch.ones(1, 1, dtype=torch.float64, device=a.cores[0].device)
+        for ca, cb in zip(a.cores, b.cores):
+            f = torch.einsum("ab,aic,bid->cd", f, ca.double(), cb.double())
+        return f[0, 0]
+
     def round(self, eps: float = 1e-14, **kwargs):
-        """tensor.py:2085-2098: TT rounding, then Tucker rounding with the left-over budget.  Only the TT
-        stage is built (Tucker factors are a 'next' row of SURVEY.md §8f)."""
+        """tensor.py:2085-2098: TT rounding, then Tucker rounding with the left-over error budget."""
+        copy = self.clone()
         self.round_tt(eps, **kwargs)
+        d = (copy._tt_dot(copy) + self._tt_dot(self) - 2 * copy._tt_dot(self)).clamp(min=0)
+        reached = float(torch.sqrt(d) / torch.sqrt(copy._tt_dot(copy).clamp(min=0)))  # metrics.relative_error
+        if reached < eps:
+            kw = {k: v for k, v in kwargs.items() if k in ("rmax", "algorithm")}
+            self.round_tucker((1 + eps) / (1 + reached) - 1, **kw)
