@@ -84,16 +84,18 @@ __global__ void __launch_bounds__(JACOBI_THREADS) jacobi_eigh_kernel(const doubl
                                                                      double* __restrict__ w_out,
                                                                      double* __restrict__ V_out,
                                                                      R* __restrict__ scratch, int max_sweeps,
-                                                                     R tol, int* __restrict__ info) {
+                                                                     R tol, int* __restrict__ info, int v_in_smem) {
   extern __shared__ __align__(16) unsigned char jac_smem_raw[];
   const int np = n + (n & 1);
   const int m = np >> 1;
   const int ld = np + 8;  // padded column stride: the lane groups of a warp hit different banks
   R* Wt;  // column-major: Wt[c*ld + r] = W[r][c]
   R* Vt;
+  // SMEM: W (the matrix every round reads three inner products from) lives in shared memory; V joins it when
+  // both fit (v_in_smem), otherwise V stays in the L1/L2-backed global scratch (it is only touched by rotations)
   if (SMEM) {
     Wt = reinterpret_cast<R*>(jac_smem_raw);
-    Vt = Wt + (size_t)np * ld;
+    Vt = v_in_smem ? Wt + (size_t)np * ld : scratch;
   } else {
     Wt = scratch;
     Vt = scratch + (size_t)np * ld;
@@ -258,15 +260,15 @@ inline size_t jacobi_scratch_doubles(int n) {
 
 template <typename R, bool SMEM>
 inline void jacobi_launch(int n, size_t smem, const double* G, int ldg, double* w, double* V, R* scratch, int max_sweeps,
-                          R tol, int* info, cudaStream_t st) {
+                          R tol, int* info, cudaStream_t st, int v_in_smem = 1) {
   // lanes per column pair (LANES) x elements per lane (EPL) >= n; small problems use 8 lanes (4 pairs per warp)
   // the block is sized to the warps that own a pair (idle warps would only lengthen every barrier)
   if (n <= 64)
-    jacobi_eigh_kernel<R, SMEM, 8, 8><<<1, 256, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 8, 8><<<1, 256, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info, v_in_smem);
   else if (n <= 128)
-    jacobi_eigh_kernel<R, SMEM, 8, 16><<<1, 512, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 8, 16><<<1, 512, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info, v_in_smem);
   else
-    jacobi_eigh_kernel<R, SMEM, 16, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info);
+    jacobi_eigh_kernel<R, SMEM, 16, 16><<<1, JACOBI_THREADS, smem, st>>>(G, n, ldg, w, V, scratch, max_sweeps, tol, info, v_in_smem);
 }
 
 // G: n x n fp64 (ld = ldg). w: n, V: n x n. scratch: jacobi_scratch_doubles(n) doubles.
@@ -291,16 +293,20 @@ inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, do
   }
   if (single_precision) {
     const float tol = loose_tol > 0.0 ? (float)loose_tol : 2e-6f;  // default ~ eps_fp32 * sqrt(n)
-    const size_t smem = (size_t)2 * np * (np + 8) * sizeof(float);
-    if (smem <= (size_t)maxb)
-      jacobi_launch<float, true>(n, smem, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
+    const size_t one = (size_t)np * (np + 8) * sizeof(float);
+    if (2 * one <= (size_t)maxb)
+      jacobi_launch<float, true>(n, 2 * one, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st, 1);
+    else if (one <= (size_t)maxb)
+      jacobi_launch<float, true>(n, one, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st, 0);
     else
       jacobi_launch<float, false>(n, 0, G, ldg, w, V, reinterpret_cast<float*>(scratch), max_sweeps, tol, info, st);
   } else {
     const double tol = loose_tol > 0.0 ? loose_tol : 1e-14;  // relative threshold |w_p.w_q| <= tol*|w_p||w_q|
-    const size_t smem = (size_t)2 * np * (np + 8) * sizeof(double);
-    if (smem <= (size_t)maxb)
-      jacobi_launch<double, true>(n, smem, G, ldg, w, V, scratch, max_sweeps, tol, info, st);
+    const size_t one = (size_t)np * (np + 8) * sizeof(double);
+    if (2 * one <= (size_t)maxb)
+      jacobi_launch<double, true>(n, 2 * one, G, ldg, w, V, scratch, max_sweeps, tol, info, st, 1);
+    else if (one <= (size_t)maxb)
+      jacobi_launch<double, true>(n, one, G, ldg, w, V, scratch, max_sweeps, tol, info, st, 0);
     else
       jacobi_launch<double, false>(n, 0, G, ldg, w, V, scratch, max_sweeps, tol, info, st);
   }

@@ -121,6 +121,37 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
       TNB_TRY((gemm_splitk<T, T, double, double, float>(pl, cols, cols, rowsA, cur, cols, false, cur, cols, false, partial,
                                                         G, cols, 1.0, nullptr, 0, 0.0, nullptr, 0, 0.0, true,
                                                         (float*)nullptr, 0, st)));
+      // fast path: Cholesky-QR in fp64 (A = Q R with R = L^T from G = L L^T); a breakdown pivot (rank-deficient
+      // or short core) raises the flag and the eigen-decomposition path below takes over for this core
+      bool chol_ok = false;
+      if (rowsA >= cols) {
+        TNB_CUDA(cudaMemsetAsync(jinfo, 0, 4 * sizeof(int), st));
+        const size_t csm = (size_t)2 * cols * (cols | 1) * sizeof(double);
+        const bool fits = csm <= (size_t)180 * 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+          TNB_CUDA(cudaFuncSetAttribute(chol_orth_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+          attr_set = true;
+        }
+        chol_orth_kernel<T><<<1, 1024, fits ? csm : 0, st>>>(G, (int)cols, js, fac, jinfo + 1, fits ? 1 : 0, Rf);
+        TNB_LAUNCH_CHECK();
+        TNB_CUDA(cudaMemcpyAsync(cx.h_sc, jinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        TNB_CUDA(cudaStreamSynchronize(st));
+        chol_ok = (cx.h_sc[1] == 0);
+      }
+      if (chol_ok) {
+        const int64_t q = cols;
+        r[k + 1] = q;
+        TNB_TRY((gemm_direct<T, T, T, T>(rowsA, q, cols, cur, cols, true, fac, q, false, Q[k], q, (T)1, nullptr, 0, (T)0,
+                                         nullptr, 0, (T)0, st)));
+        const int64_t ncols = d.shape[k + 1] * d.rin[k + 2];
+        TNB_TRY((gemm_direct<T, T, T, T>(q, ncols, cols, Rf, cols, true, cores_in[k + 1], ncols, false, nxt, ncols, (T)1,
+                                         nullptr, 0, (T)0, nullptr, 0, (T)0, st)));
+        T* t = cur; cur = nxt; nxt = t;
+        if (ar.off > peak) peak = ar.off;
+        ar.off = mark;
+        continue;
+      }
       TNB_TRY(jacobi_eigh(G, (int)cols, (int)cols, w, V, js, jinfo, st));
       const int64_t cap = std::min<int64_t>(rowsA, cols);
       rank_thresh_kernel<<<1, 32, 0, st>>>(w, (int)cols, 64.0 * 2.220446049250313e-16, (int)cap, cx.sc);

@@ -168,7 +168,8 @@ __global__ void svqb_finish_kernel(const double* __restrict__ Q, const double* _
 // falls back to the eigen-decomposition based SVQB transform.
 template <typename TB>
 __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restrict__ S, int b, double* scratch,
-                                                         TB* __restrict__ T, int* flag, int use_smem) {
+                                                         TB* __restrict__ T, int* flag, int use_smem,
+                                                         TB* __restrict__ Rout = nullptr) {
   extern __shared__ __align__(16) unsigned char chol_smem_raw[];
   __shared__ double s_d[JACOBI_MAX_N];
   __shared__ double s_piv[JACOBI_MAX_N];
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
   for (int idx = tid; idx < b * b; idx += nt) {
     const int i = idx / b, j = idx % b;
     T[idx] = (TB)((j >= i) ? s_d[i] * Li[(size_t)j * ld + i] : 0.0);
+    // the matching triangular factor R = L^T D^-1 (A = (A T) R): R[i][j] = L[j][i] / d_j
+    if (Rout) Rout[idx] = (TB)((j >= i && s_d[j] > 0.0) ? L[(size_t)j * ld + i] / s_d[j] : 0.0);
   }
 }
 
