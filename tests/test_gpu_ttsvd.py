@@ -24,8 +24,10 @@ def _run(name, use_tc=True):
     X = cases.make_dense(spec)
     Xd = torch.as_tensor(X).cuda()
     if spec.get("eps") is not None:
-        t = tnb.Tensor(Xd, eps=spec["eps"])
-        cores = t.cores
+        t = tnb.Tensor(Xd, eps=spec["eps"])  # = round_tt + round_tucker in the reference (tensor.py:436-439)
+        ranks = list(t.ranks_tt)
+        cores = t.decompress_tucker_factors().cores
+        assert ranks_of(cores) == ranks
     else:
         cores = ops.ttsvd(Xd, rmax=spec["ranks_tt"], use_tensorcore=use_tc)
     return X, cores
