@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--per-gpu-batch", type=int, default=4,
                     help="independent tensors decomposed concurrently per GPU (one CUDA stream + host thread each): the "
                          "latency-bound eigen phases of one overlap the bandwidth-bound Gram/projection phases of another")
+    ap.add_argument("--no-concurrent-flag", action="store_true",
+                    help="A/B: do not pass TNB_FLAG_CONCURRENT when several tensors are in flight")
     return ap.parse_args()
 
 
@@ -220,7 +222,8 @@ def run_ours(args):
     for b in range(PB):
         g = torch.Generator(device=dev).manual_seed(1234 + rank_id * 16 + b)
         Xs.append(torch.randn(shape, generator=g, device=dev, dtype=torch.float32))  # 4 GiB each >> 126 MB L2
-        plans.append(ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc))
+        plans.append(ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc,
+                                   concurrent=(PB > 1 and not args.no_concurrent_flag)))
         streams.append(torch.cuda.Stream(device=dev))
     X, plan = Xs[0], plans[0]
     prof_plan = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, profile=True)

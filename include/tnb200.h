@@ -41,6 +41,9 @@ extern "C" {
 #define TNB_FLAG_NO_TENSORCORE 1u /* force the generic fp32/fp64 CUDA-core kernels (debug / parity A-B) */
 #define TNB_FLAG_BATCH_MODE 2u    /* reference `batch=True` rank rule: rank = min(rmax, len(S)), no eps  */
 #define TNB_FLAG_PROFILE 4u       /* record CUDA events around each phase; timings returned in info_host  */
+#define TNB_FLAG_CONCURRENT 8u    /* the caller runs several decompositions at once on different streams: the
+                                    latency-bound eigen-iteration kernels then use few SMs (one CTA per output
+                                    tile) instead of the whole GPU, leaving the rest to the other streams   */
 
 int tnb_version(void);
 const char* tnb_last_error(void);
@@ -65,7 +68,8 @@ int tnb_has_tensorcore_path(void);
  *   ranks_host ndim+1 ints (host), ranks_host[0] = ranks_host[ndim] = 1
  *   info_host  optional (may be NULL) 32 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix products,
  *              [3]=#tensor-core Gram launches; with TNB_FLAG_PROFILE also [4]=Gram ms, [5]=eigen ms,
- *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 8
+ *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 7;
+ *              [31]=#Chebyshev filters that ran as one resident cluster kernel
  * ------------------------------------------------------------------------------------------ */
 int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host);
 size_t tnb_ttsvd_workspace_bytes(int dtype, int ndim, const int64_t* shape, const int32_t* rmax, uint32_t flags);
@@ -165,6 +169,17 @@ int tnb_gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, void* wo
 size_t tnb_atb_tc_workspace_bytes(int64_t K, int64_t m, int64_t n);
 int tnb_atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t n, float* C, float alpha,
                    const float* D, float beta, void* workspace, size_t workspace_bytes, void* stream);
+/* Chebyshev filter of the subspace iteration as ONE resident cluster kernel: `steps` products
+ * Y_s = a[s-1] * G*Y_{s-1} + bc[s-1] * Y_{s-1} + g[s-1] * Y_{s-2}  (G symmetric n x n fp32, TF32 operands,
+ * blocks n x b fp32).  G stays partitioned over the shared memories of the grid for all steps; clusters of 8
+ * CTAs reduce their partial tiles through distributed shared memory.  bufs = three n x b device blocks,
+ * bufs[0] = Y_0 on entry; the result is left in bufs[steps % 3].  n % 256 == 0, n <= 2048, b % 4 == 0,
+ * steps <= 48.  When 8-CTA clusters for all slabs cannot be co-resident (n = 2048 on B200) the partial tiles go
+ * through L2 with a second grid barrier per step.  TNB_ERR_UNSUPPORTED outside that envelope. */
+size_t tnb_cheb_filter_workspace_bytes(int32_t n, int32_t b);
+int tnb_cheb_filter_f32(const float* G, int32_t n, int32_t b, float* buf0, float* buf1, float* buf2, int32_t steps,
+                        const float* a_host, const float* bc_host, const float* g_host, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* C (rows x r) = A (rows x n) * V (n x r), same dtype throughout (fp32: FFMA, fp32 accumulate).
  * Replaces: `M @ left` round.py:181 / einsum absorb tensor.py:2081-2083. */
 int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream);

@@ -84,3 +84,62 @@ def test_project_tc_fp32_accuracy(shape):
     Cf = ops.project(A, V)  # FFMA kernel for comparison
     errf = (Cf.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 20 * max(errf, 1e-7)
+
+
+@pytest.mark.parametrize("n,b,steps", [(256, 32, 3), (512, 64, 5), (1024, 64, 17), (2048, 64, 40), (1536, 40, 7)])
+@pytest.mark.parametrize("dsmem", [True, False])
+def test_resident_chebyshev_filter(n, b, steps, dsmem, monkeypatch):
+    """cheb_filter.cuh: the whole three-term recurrence in one cooperative kernel vs fp64 torch; partial tiles
+    reduced through distributed shared memory (clusters of 8) or through L2 (forced here for every size)."""
+    from tntorch_b200 import ops
+
+    if not dsmem:
+        monkeypatch.setenv("TNB_FILTER_NO_DSMEM", "1")
+
+    gen = torch.Generator().manual_seed(n + b)
+    A = torch.randn(n, n, generator=gen, dtype=torch.float64)
+    G = (A @ A.T / n).cuda()
+    Y0 = torch.randn(n, b, generator=gen, dtype=torch.float64).cuda()
+    lam = float(torch.linalg.matrix_norm(G, 2))
+    # a damped recurrence (|a lam| + |bc| + |g| < 1.5) so that 40 steps stay O(1)
+    a = [0.9 / lam] * steps
+    bc = [-0.3] * steps
+    g = [0.0] + [-0.25] * (steps - 1)
+    out = ops.cheb_filter(G.float(), Y0.float(), a, bc, g)
+    prev, cur = None, Y0
+    for s in range(steps):
+        nxt = a[s] * (G @ cur) + bc[s] * cur + (g[s] * prev if prev is not None else 0)
+        prev, cur = cur, nxt
+    err = float((out.double() - cur).norm() / cur.norm())
+    assert err < 1e-3 * max(steps, 5), err  # TF32 operand truncation accumulates over the steps
+
+
+def test_sweep_uses_resident_filter():
+    from oracle import cases
+    from tntorch_b200 import ops
+
+    spec = cases.TTSVD_CASES["randn64x4_r32_f32"]
+    X = torch.as_tensor(cases.make_dense(spec)).cuda()
+    _, info = ops.ttsvd(X, rmax=spec["ranks_tt"], return_info=True)
+    assert info["fused_filters"] >= 1, info
+
+
+@pytest.mark.parametrize("name", ["twin32x5_r32_f32", "randn64x4_r32_f32"])
+def test_concurrent_flag_same_result(name):
+    """TNB_FLAG_CONCURRENT only changes how the eigen-iteration products are scheduled (one CTA per output
+    tile, direct epilogue): ranks and error must match the golden vectors just the same."""
+    import os
+
+    import numpy as np
+    from gpu_util import ranks_of, relerr64
+    from oracle import cases
+    from tntorch_b200 import ops
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ttsvd.npz"))
+    spec = cases.TTSVD_CASES[name]
+    X = cases.make_dense(spec)
+    cores, info = ops.ttsvd(torch.as_tensor(X).cuda(), rmax=spec["ranks_tt"], return_info=True, concurrent=True)
+    alg = "svd" if f"{name}/svd/relerr" in g.files else "eig"
+    assert ranks_of(cores) == list(g[f"{name}/{alg}/ranks"])
+    assert abs(relerr64(X, cores) - float(g[f"{name}/{alg}/relerr"])) <= 1e-5
+    assert info["fused_filters"] == 0

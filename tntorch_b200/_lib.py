@@ -16,6 +16,7 @@ TNB_F32, TNB_F64 = 0, 1
 FLAG_NO_TENSORCORE = 1
 FLAG_BATCH_MODE = 2
 FLAG_PROFILE = 4
+FLAG_CONCURRENT = 8
 
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOCONV = 1, 2, 3, 4, 5
 
@@ -67,6 +68,9 @@ SIGNATURES = {
     "tnb_atb_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "tnb_atb_tc_f32": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_float, _vp, C.c_float, _vp,
                                  C.c_size_t, _vp]),
+    "tnb_cheb_filter_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "tnb_cheb_filter_f32": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_size_t,
+                                      _vp]),
     "tnb_project": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp]),
     "tnb_project_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "tnb_project_tc_f32": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp, C.c_size_t, _vp]),

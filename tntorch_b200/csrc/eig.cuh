@@ -10,12 +10,14 @@
 #include "common.cuh"
 #include "gemm_generic.cuh"
 #include "gram_tc.cuh"
+#include "cheb_filter.cuh"
 #include "jacobi.cuh"
 #include "small_kernels.cuh"
 
 namespace tnb {
 
 struct ChfsiStats {
+  int fused_filters = 0;  // filters that ran as one resident kernel (cheb_filter.cuh)
   int products = 0;  // number of G*X block products
   int outer = 0;
   int converged = 0;
@@ -35,6 +37,7 @@ struct ChfsiWork {
   void* partial;            // split-K scratch, partial_bytes
   size_t partial_bytes;
   bool use_tc = false;      // filter products on the tcgen05 kernel (fp32 blocks only)
+  bool narrow = false;      // TNB_FLAG_CONCURRENT: products on one CTA per output tile, no resident whole-GPU filter
   double *S, *lam, *Q, *d;  // b*b, b, b*b, b
   double* jscratch;         // jacobi_scratch_doubles(b)
   int* jinfo;
@@ -56,6 +59,8 @@ inline void chfsi_carve(ArenaT& ar, int n, int b, ChfsiWork<TB>& w) {
   if (std::is_same<TB, float>::value && atb_tc_shape_ok(n, n, b)) {
     const size_t e3 = atb_tc_workspace_bytes(n, n, b);
     if (e3 > w.partial_bytes) w.partial_bytes = e3;
+    if (cheb_filter_shape_ok(n, b) && cheb_filter_workspace_bytes(n, b) > w.partial_bytes)
+      w.partial_bytes = cheb_filter_workspace_bytes(n, b);
   }
   w.partial = ar.template take<char>(w.partial_bytes);
   w.S = ar.template take<double>((size_t)b * b);
@@ -63,7 +68,7 @@ inline void chfsi_carve(ArenaT& ar, int n, int b, ChfsiWork<TB>& w) {
   w.Q = ar.template take<double>((size_t)b * b);
   w.d = ar.template take<double>(b);
   w.jscratch = ar.template take<double>(jacobi_scratch_doubles(b));
-  w.jinfo = ar.template take<int>(4);
+  w.jinfo = ar.template take<int>(4);  // [0] Jacobi sweeps, [1] Cholesky breakdown flag
 }
 
 // Y <- a * G*Yin + bc * Yin + g * Xin      (G symmetric, stored n x n in TB)
@@ -77,7 +82,7 @@ inline int chfsi_apply(const TB* G, int n, int b, const TB* Yin, const TB* Xin, 
     return atb_tc_f32(reinterpret_cast<const float*>(G), n, n, reinterpret_cast<const float*>(Yin), b,
                       reinterpret_cast<float*>(Yout), b, (float)a, (bc != 0.0 ? reinterpret_cast<const float*>(Yin) : nullptr),
                       b, (float)bc, (g != 0.0 ? reinterpret_cast<const float*>(Xin) : nullptr), b, (float)g, w.partial,
-                      w.partial_bytes, st);
+                      w.partial_bytes, st, w.narrow);
   GemmPlan pl = plan_gemm(n, b, n, false);
   return gemm_splitk<TB, TB, TB, TB, TB>(pl, n, b, n, G, n, /*a_kmaj (symmetric: either)*/ false, Yin, b, false,
                                          reinterpret_cast<TB*>(w.partial), Yout, b, (TB)a, (bc != 0.0 ? Yin : nullptr), b,
@@ -215,16 +220,39 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
       for (int q = 0; q < 3; ++q)
         if (all3[q] != X) bufs[c3++] = all3[q];
     }
-    // Y = (G X - c X) * sigma1/e
-    TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[0], nullptr, bufs[1], sigma1 / e, -c * sigma1 / e, 0.0, w, st, true));
-    int iprev = 0, icur = 1, inew = 2;
-    for (int i = 2; i <= m; ++i) {
-      const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
-      // Ynew = 2 sigma2/e (G Y - c Y) - sigma sigma2 Xprev
-      TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[icur], bufs[iprev], bufs[inew], 2.0 * sigma2 / e, -2.0 * sigma2 * c / e,
-                              -sigma * sigma2, w, st, true));
-      const int t = iprev; iprev = icur; icur = inew; inew = t;
-      sigma = sigma2;
+    bool fused = false;
+    if (w.use_tc && !w.narrow && std::is_same<TB, float>::value && m <= CF_MAX_STEPS) {
+      // the whole filter as one resident kernel (cheb_filter.cuh); same recurrence, coefficients precomputed
+      float fa[CF_MAX_STEPS], fb[CF_MAX_STEPS], fg[CF_MAX_STEPS];
+      double sg = sigma1;
+      fa[0] = (float)(sigma1 / e); fb[0] = (float)(-c * sigma1 / e); fg[0] = 0.f;
+      for (int i = 2; i <= m; ++i) {
+        const double sigma2 = 1.0 / (2.0 / sigma1 - sg);
+        fa[i - 1] = (float)(2.0 * sigma2 / e); fb[i - 1] = (float)(-2.0 * sigma2 * c / e); fg[i - 1] = (float)(-sg * sigma2);
+        sg = sigma2;
+      }
+      float* fbufs[3] = {reinterpret_cast<float*>(bufs[0]), reinterpret_cast<float*>(bufs[1]), reinterpret_cast<float*>(bufs[2])};
+      const int rc = cheb_filter_f32(reinterpret_cast<const float*>(G), n, b, fbufs, m, fa, fb, fg, w.partial,
+                                     w.partial_bytes, st);
+      if (rc == TNB_OK) fused = true;
+      else if (rc != TNB_ERR_UNSUPPORTED) return rc;
+    }
+    int icur = m % 3, inew = (m + 1) % 3;
+    if (fused) {
+      if (stats) stats->fused_filters += 1;
+    } else {
+      // Y = (G X - c X) * sigma1/e
+      TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[0], nullptr, bufs[1], sigma1 / e, -c * sigma1 / e, 0.0, w, st, true));
+      int iprev = 0;
+      icur = 1; inew = 2;
+      for (int i = 2; i <= m; ++i) {
+        const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+        // Ynew = 2 sigma2/e (G Y - c Y) - sigma sigma2 Xprev
+        TNB_TRY(chfsi_apply<TB>(G, n, b, bufs[icur], bufs[iprev], bufs[inew], 2.0 * sigma2 / e, -2.0 * sigma2 * c / e,
+                                -sigma * sigma2, w, st, true));
+        const int t = iprev; iprev = icur; icur = inew; inew = t;
+        sigma = sigma2;
+      }
     }
     if (stats) stats->products += m + 1;
     X = bufs[icur];

@@ -3,29 +3,35 @@
 // i.e. the accuracy class of an fp32 FFMA product — a plain TF32 projection would put a 2^-11 relative error
 // straight into the reconstruction).  This is the "C <- C V_r" step of the sweep (round.py:181, tensor.py:2081-2083).
 //
-//   * A row blocks (128 rows x 32 k) are staged by TMA (K-major, SWIZZLE_128B), 4-stage mbarrier ring; the matching
-//     V_hi^T / V_lo^T chunks (r x 32 k) ride in the same stage;
-//   * the tensor core truncates fp32 operands to TF32 itself, so A_hi is the raw tile; A_lo = A - trunc(A) is
-//     produced by four "split" warps straight on the swizzled bytes (an elementwise map keeps the layout) into a
-//     second buffer, fenced into the async proxy;
-//   * one elected thread issues 3 x (32/8) tcgen05.mma.kind::tf32 (M=128, N=r_pad, K=8) per stage into one of
-//     four TMEM accumulator slots; four epilogue warps drain finished tiles (tcgen05.ld) to global while the
-//     next row block is already being multiplied (persistent CTAs, static round-robin over row blocks).
+//   * A row blocks (128 rows x 32 k) are staged by TMA (K-major, SWIZZLE_128B), 6-stage mbarrier ring; the matching
+//     V_hi^T / V_lo^T chunks (r x 32 k) ride in the same stage, stacked as ONE B operand of 2*r_pad rows;
+//   * the tensor core truncates fp32 operands to TF32 itself, so A_hi is the raw tile: one SS MMA
+//     A x [V_hi; V_lo] (N = 2*r_pad) gives A_hi V_hi and A_hi V_lo side by side in TMEM;
+//   * A_lo = A - trunc(A) is produced by four "split" warps (thread = row, conflict-free reads of the swizzled
+//     tile) and written to TENSOR MEMORY (tcgen05.st), from where a TS MMA (A operand in TMEM) adds A_lo V_hi
+//     onto the first r_pad accumulator columns — the tile crosses the shared-memory port three times (TMA fill,
+//     split read, MMA read) instead of six;
+//   * four epilogue warps drain finished tiles (tcgen05.ld), add the two halves and store, while the next row
+//     block is already being multiplied (persistent CTAs, static round-robin over row blocks).
 //
-// Bound: HBM (reads A once: 4 B/element for 2*r flop) — the three MMAs per k-step cost 3*128*r*8 MACs per
-// 128x8 elements, far below the tensor-pipe limit; the shared-memory pipe (TMA fill + split read/write + 3 MMA
-// operand reads) is the secondary limit.
+// Bound: HBM (reads A once: 4 B/element for 2*r flop) — the MMAs cost 3*128*r*8 MACs per 128x8 elements, far
+// below the tensor-pipe limit; the shared-memory port (68 KB moved per 16 KB tile) stays below the HBM feed.
 #pragma once
 #include "gram_tc.cuh"
 
 namespace tnb {
 
-constexpr int PT_BM = 128, PT_KC = 32, PT_STAGES = 4, PT_ACC_SLOTS = 4, PT_THREADS = 320;
+constexpr int PT_BM = 128, PT_KC = 32, PT_MAX_STAGES = 12, PT_THREADS = 320;
 constexpr int PT_A_BYTES = PT_BM * PT_KC * 4;      // 16 KB
 constexpr int PT_MAX_N = 64;                        // r padded to a multiple of 16, <= 64
-constexpr int PT_B_BYTES = PT_MAX_N * PT_KC * 4;    // 8 KB slot per V part
-constexpr int PT_STAGE_BYTES = 2 * PT_A_BYTES + 2 * PT_B_BYTES;  // A, A_lo, Vhi, Vlo
-constexpr int PT_SMEM_BYTES = PT_STAGES * PT_STAGE_BYTES + 1024 + 512;
+constexpr int PT_RING_BYTES = 192 * 1024;           // stage ring (+ resident V when it fits)
+constexpr int PT_SMEM_BYTES = PT_RING_BYTES + 1024 + 512;
+constexpr int PT_VRES_MAX_BYTES = 32 * 1024;        // V_hi|V_lo kept in shared memory for the whole kernel up to this size
+constexpr int PT_ACC_COLS = 256;                    // accumulator slots: 256 / (2*npad) of width 2*npad
+constexpr int PT_ALO_COL = PT_ACC_COLS;             // A_lo ring: PT_ALO_SLOTS x 32 columns behind the accumulators
+constexpr int PT_ALO_SLOTS = 8;  // 8 x 32 columns: with the 256 accumulator columns exactly the 512 of an SM
+constexpr int PT_TMEM_COLS = 512;
+constexpr int PT_MAX_SLOTS = 8;
 
 struct ProjTcParams {
   int64_t rows;
@@ -37,6 +43,10 @@ struct ProjTcParams {
   int slab;    // chunks per accumulator slab: the TMEM accumulator truncates on every add, so long K ranges are cut
                // into slabs of PT_SLAB_CHUNKS*32 columns whose partial tiles are summed in fp32 (RN) by the epilogue
   int nslabs;
+  int vres;         // 1: all V chunks resident in shared memory (small K), stages hold A only
+  int stage_bytes;  // 16 KB (+ 2*npad*128 B of V chunk when streaming V)
+  int nstages;      // ring depth that fits PT_RING_BYTES: the HBM latency needs >= ~140 KB in flight per SM
+  int alo_slots;    // A_lo ring depth in use (<= PT_ALO_SLOTS)
   float* C;
 };
 constexpr int PT_SLAB_CHUNKS = 8;
@@ -64,6 +74,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// D[tmem] += A[tmem] * B[smem]  (A operand read from tensor memory: lane = row, column = k)
+__device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(PT_THREADS, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_vhi,
@@ -72,29 +106,39 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t raw_addr = smem_u32(pt_smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   unsigned char* stage_base = pt_smem_raw + pad;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + PT_STAGES * PT_STAGE_BYTES);
-  uint64_t* split_bar = full_bar + PT_STAGES;
-  uint64_t* empty_bar = split_bar + PT_STAGES;
-  uint64_t* acc_full = empty_bar + PT_STAGES;
-  uint64_t* acc_empty = acc_full + PT_ACC_SLOTS;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + PT_ACC_SLOTS);
+  unsigned char* v_res = stage_base + (size_t)p.nstages * p.stage_bytes;   // resident V (vres): nk x [V_hi; V_lo] chunks
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + PT_RING_BYTES);
+  uint64_t* empty_bar = full_bar + PT_MAX_STAGES;
+  uint64_t* alo_full = empty_bar + PT_MAX_STAGES;
+  uint64_t* alo_empty = alo_full + PT_ALO_SLOTS;
+  uint64_t* acc_full = alo_empty + PT_ALO_SLOTS;
+  uint64_t* acc_empty = acc_full + PT_MAX_SLOTS;
+  uint64_t* v_bar = acc_empty + PT_MAX_SLOTS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(v_bar + 1);
+  const int slot_w = 2 * p.npad;                 // A_hi V_hi (+ A_lo V_hi) | A_hi V_lo
+  const int nslots = PT_ACC_COLS / slot_w;       // 8 (npad 16) .. 2 (npad 64)
+  const int vchunk_bytes = 2 * p.npad * PT_KC * 4;
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PT_STAGES; ++s) {
+    for (int s = 0; s < PT_MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);   // one arrival per split warp
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < PT_ACC_SLOTS; ++s) {
+    for (int s = 0; s < PT_ALO_SLOTS; ++s) {
+      mbar_init(&alo_full[s], 4);    // one arrival per split warp
+      mbar_init(&alo_empty[s], 1);
+    }
+    for (int s = 0; s < PT_MAX_SLOTS; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
     }
+    mbar_init(v_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp_idx == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)(PT_ACC_SLOTS * PT_MAX_N))
+                 "r"((uint32_t)PT_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -109,108 +153,134 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp_idx == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)PT_A_BYTES + 2u * (uint32_t)(p.npad * PT_KC * 4);
+      if (p.vres && total_items > 0) {
+        mbar_expect_tx(v_bar, (uint32_t)(p.nk * vchunk_bytes));
+        for (int kc = 0; kc < p.nk; ++kc) {
+          tma_load_2d(v_res + (size_t)kc * vchunk_bytes, &tmap_vhi, v_bar, kc * PT_KC, 0);
+          tma_load_2d(v_res + (size_t)kc * vchunk_bytes + p.npad * PT_KC * 4, &tmap_vlo, v_bar, kc * PT_KC, 0);
+        }
+      }
+      const uint32_t tx_bytes = (uint32_t)PT_A_BYTES + (p.vres ? 0u : (uint32_t)vchunk_bytes);
       int stage = 0;
       uint32_t phase = 0;
+      int kc = 0;
+      int row0 = (int)blockIdx.x * PT_BM;           // rows < 2^31 (checked on the host)
+      const int row_step = (int)gridDim.x * PT_BM;
       for (int64_t item = 0; item < total_items; ++item) {
-        const int64_t rb = blockIdx.x + (item / p.nk) * (int64_t)gridDim.x;
-        const int kc = (int)(item % p.nk);
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        unsigned char* sb = stage_base + stage * PT_STAGE_BYTES;
+        unsigned char* sb = stage_base + (size_t)stage * p.stage_bytes;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
-        tma_load_2d(sb, &tmap_a, &full_bar[stage], kc * PT_KC, (int)(rb * PT_BM));
-        tma_load_2d(sb + 2 * PT_A_BYTES, &tmap_vhi, &full_bar[stage], kc * PT_KC, 0);
-        tma_load_2d(sb + 2 * PT_A_BYTES + PT_B_BYTES, &tmap_vlo, &full_bar[stage], kc * PT_KC, 0);
-        if (++stage == PT_STAGES) { stage = 0; phase ^= 1u; }
+        tma_load_2d(sb, &tmap_a, &full_bar[stage], kc * PT_KC, row0);
+        if (!p.vres) {
+          tma_load_2d(sb + PT_A_BYTES, &tmap_vhi, &full_bar[stage], kc * PT_KC, 0);
+          tma_load_2d(sb + PT_A_BYTES + p.npad * PT_KC * 4, &tmap_vlo, &full_bar[stage], kc * PT_KC, 0);  // rows npad..2npad-1
+        }
+        if (++kc == p.nk) { kc = 0; row0 += row_step; }
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp_idx == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_kk(PT_BM, p.npad);
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t idesc2 = make_idesc_tf32_kk(PT_BM, 2 * p.npad);  // A x [V_hi; V_lo]
+      const uint32_t idesc1 = make_idesc_tf32_kk(PT_BM, p.npad);      // A_lo x V_hi
+      int stage = 0, aslot = 0, slot = 0, sl = 0;
+      uint32_t phase = 0, aphase = 0, acc_phase = 0;
       const int64_t tiles = my_blocks * p.nslabs;
-      for (int64_t tile = 0; tile < tiles; ++tile) {
-        const int slot = (int)(tile % PT_ACC_SLOTS);
-        const uint32_t acc_phase = (uint32_t)((tile / PT_ACC_SLOTS) & 1);
-        const int sl = (int)(tile % p.nslabs);
+      if (p.vres && tiles > 0) mbar_wait(v_bar, 0);
+      // descriptors differ only in the 14-bit start-address field: build the constant part once
+      const uint64_t desc_hi = make_k_major_desc(0);
+      const uint32_t stage0 = smem_u32(stage_base), vres0 = smem_u32(v_res);
+      for (int64_t tile = 0; tile < tiles; ++tile) {  // no 64-bit divisions in here: this one thread paces the CTA
         const int kc_begin = sl * p.slab, kc_end = (kc_begin + p.slab < p.nk) ? kc_begin + p.slab : p.nk;
         mbar_wait(&acc_empty[slot], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(slot * PT_MAX_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(slot * slot_w);
         for (int kc = kc_begin; kc < kc_end; ++kc) {
-          const uint32_t sb = smem_u32(stage_base + stage * PT_STAGE_BYTES);
+          const uint32_t sb = stage0 + (uint32_t)(stage * p.stage_bytes);
+          const uint32_t vb = p.vres ? vres0 + (uint32_t)(kc * vchunk_bytes) : sb + PT_A_BYTES;
+          const uint64_t ad = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF), bd = desc_hi | (uint64_t)((vb >> 4) & 0x3FFF);
+          const uint32_t alo = tmem_base + (uint32_t)(PT_ALO_COL + aslot * PT_KC);
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < PT_KC / 8; ++ks) {  // A_hi (raw, truncated by the tensor core) x V_hi, x V_lo
-            const uint64_t a = make_k_major_desc(sb + ks * 32u);
-            tcgen05_mma_tf32(tmem_d, a, make_k_major_desc(sb + 2 * PT_A_BYTES + ks * 32u), idesc, (kc > kc_begin || ks > 0) ? 1u : 0u);
-            tcgen05_mma_tf32(tmem_d, a, make_k_major_desc(sb + 2 * PT_A_BYTES + PT_B_BYTES + ks * 32u), idesc, 1u);
-          }
-          mbar_wait(&split_bar[stage], phase);  // A_lo written and fenced
+          // A_hi (raw, truncated by the tensor core) x [V_hi; V_lo]; one k-step = 32 B = +2 in the address field
+          tcgen05_mma_tf32(tmem_d, ad, bd, idesc2, kc > kc_begin ? 1u : 0u);
+          tcgen05_mma_tf32(tmem_d, ad + 2, bd + 2, idesc2, 1u);
+          tcgen05_mma_tf32(tmem_d, ad + 4, bd + 4, idesc2, 1u);
+          tcgen05_mma_tf32(tmem_d, ad + 6, bd + 6, idesc2, 1u);
+          mbar_wait(&alo_full[aslot], aphase);  // A_lo of this chunk is in tensor memory
           tcgen05_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < PT_KC / 8; ++ks)
-            tcgen05_mma_tf32(tmem_d, make_k_major_desc(sb + PT_A_BYTES + ks * 32u),
-                             make_k_major_desc(sb + 2 * PT_A_BYTES + ks * 32u), idesc, 1u);
-          tcgen05_commit(&empty_bar[stage]);
-          if (++stage == PT_STAGES) { stage = 0; phase ^= 1u; }
+          tcgen05_mma_tf32_ts(tmem_d, alo, bd, idesc1, 1u);
+          tcgen05_mma_tf32_ts(tmem_d, alo + 8, bd + 2, idesc1, 1u);
+          tcgen05_mma_tf32_ts(tmem_d, alo + 16, bd + 4, idesc1, 1u);
+          tcgen05_mma_tf32_ts(tmem_d, alo + 24, bd + 6, idesc1, 1u);
+          tcgen05_commit(&empty_bar[stage]);   // shared-memory stage reusable
+          tcgen05_commit(&alo_empty[aslot]);   // tensor-memory A_lo slot reusable
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+          if (++aslot == p.alo_slots) { aslot = 0; aphase ^= 1u; }
         }
         tcgen05_commit(&acc_full[slot]);
+        if (++slot == nslots) { slot = 0; acc_phase ^= 1u; }
+        if (++sl == p.nslabs) sl = 0;
       }
     }
   } else if (warp_idx < 6) {
-    // ================= split warps: A_lo = A - trunc_tf32(A), elementwise on the swizzled tile =================
-    const int t = threadIdx.x - 64;  // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
+    // ================= split warps: A_lo = A - trunc_tf32(A), one row per thread, into tensor memory =================
+    const int lg = warp_idx & 3;          // TMEM lane group this warp may access
+    const int m = lg * 32 + lane;         // tile row
+    const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+    int stage = 0, aslot = 0;
+    uint32_t phase = 0, aphase = 0;
     for (int64_t item = 0; item < total_items; ++item) {
       mbar_wait(&full_bar[stage], phase);
-      const float4* src = reinterpret_cast<const float4*>(stage_base + stage * PT_STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(stage_base + stage * PT_STAGE_BYTES + PT_A_BYTES);
+      const unsigned char* a = stage_base + (size_t)stage * p.stage_bytes + row_off;
+      uint32_t lo[32];
 #pragma unroll
-      for (int i = 0; i < PT_A_BYTES / 16 / 128; ++i) {
-        const float4 v = src[t + i * 128];
-        float4 o;
-        o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        dst[t + i * 128] = o;
+      for (int u = 0; u < 8; ++u) {  // 16-byte unit u of the row sits at (u ^ (row % 8)) under SWIZZLE_128B
+        const float4 v = *reinterpret_cast<const float4*>(a + ((u ^ (m & 7)) << 4));
+        lo[4 * u + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+        lo[4 * u + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+        lo[4 * u + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+        lo[4 * u + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
       }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_wait(&alo_empty[aslot], aphase ^ 1u);  // the TS MMA that read this slot last has completed
+      tcgen05_fence_after();
+      tmem_st_32x32b_x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(PT_ALO_COL + aslot * PT_KC), lo);
+      tmem_st_wait();
+      tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&split_bar[stage]);
-      if (++stage == PT_STAGES) { stage = 0; phase ^= 1u; }
+      if (lane == 0) mbar_arrive(&alo_full[aslot]);
+      if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+      if (++aslot == p.alo_slots) { aslot = 0; aphase ^= 1u; }
     }
   } else {
     // ================= epilogue warps =================
     const int lane_group = warp_idx & 3;
     const int row_in_tile = lane_group * 32 + lane;
     const int64_t tiles = my_blocks * p.nslabs;
+    int slot = 0, sl = 0;
+    uint32_t acc_phase = 0;
+    int64_t grow = (int64_t)blockIdx.x * PT_BM + row_in_tile;
     for (int64_t tile = 0; tile < tiles; ++tile) {
-      const int slot = (int)(tile % PT_ACC_SLOTS);
-      const uint32_t acc_phase = (uint32_t)((tile / PT_ACC_SLOTS) & 1);
-      const int64_t blk = tile / p.nslabs;
-      const bool add = (tile % p.nslabs) != 0;  // later slabs of a row block add to what this warp stored before
-      const int64_t rb = blockIdx.x + blk * (int64_t)gridDim.x;
-      const int64_t grow = rb * PT_BM + row_in_tile;
+      const bool add = sl != 0;  // later slabs of a row block add to what this warp stored before
       mbar_wait(&acc_full[slot], acc_phase);
       tcgen05_fence_after();
-      for (int c0 = 0; c0 < p.npad; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(slot * PT_MAX_N + c0), v);
+      for (int c0 = 0; c0 < p.npad; c0 += 16) {
+        uint32_t v[16], w[16];
+        const uint32_t t0 = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(slot * slot_w + c0);
+        tmem_ld_32x32b_x16(t0, v);                       // A_hi V_hi + A_lo V_hi
+        tmem_ld_32x32b_x16(t0 + (uint32_t)p.npad, w);    // A_hi V_lo
         tmem_ld_wait();
         if (grow < p.rows) {
           float* out = p.C + grow * p.r + c0;
           if ((p.r & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
+            for (int q = 0; q < 4; ++q)
               if (c0 + 4 * q + 3 < p.r) {
-                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                float4 o = make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(w[4 * q]),
+                                       __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]),
+                                       __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]));
                 float4* dst = reinterpret_cast<float4*>(out + 4 * q);
                 if (add) {
                   const float4 old = *dst;
@@ -220,22 +290,26 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               }
           } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (c0 + q < p.r) out[q] = add ? out[q] + __uint_as_float(v[q]) : __uint_as_float(v[q]);
+            for (int q = 0; q < 16; ++q)
+              if (c0 + q < p.r) {
+                const float x = __uint_as_float(v[q]) + __uint_as_float(w[q]);
+                out[q] = add ? out[q] + x : x;
+              }
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      if (++slot == nslots) { slot = 0; acc_phase ^= 1u; }
+      if (++sl == p.nslabs) { sl = 0; grow += (int64_t)gridDim.x * PT_BM; }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp_idx == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(PT_ACC_SLOTS * PT_MAX_N))
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)PT_TMEM_COLS)
                  : "memory");
   }
 }
@@ -289,6 +363,12 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   p.slab = PT_SLAB_CHUNKS;
   p.nslabs = (p.nk + p.slab - 1) / p.slab;
   p.C = C;
+  const int vchunk = 2 * p.npad * PT_KC * 4;
+  p.vres = ((int64_t)p.nk * vchunk <= PT_VRES_MAX_BYTES) ? 1 : 0;
+  p.stage_bytes = PT_A_BYTES + (p.vres ? 0 : vchunk);
+  p.nstages = (PT_RING_BYTES - (p.vres ? p.nk * vchunk : 0)) / p.stage_bytes;
+  if (p.nstages > PT_MAX_STAGES) p.nstages = PT_MAX_STAGES;
+  p.alo_slots = PT_ALO_SLOTS;
   float* Vhi = static_cast<float*>(ws);
   float* Vlo = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)p.npad * K * sizeof(float)));
   split_v_kernel<<<grid_for((int64_t)p.npad * K), 256, 0, st>>>(V, (int)K, r, p.npad, Vhi, Vlo);

@@ -184,9 +184,10 @@ inline int eig_carve(ArenaT& ar, int64_t L, int64_t rcap, bool have_rmax, EigWor
 
 template <typename TBk>
 inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e, const double* d_trace,
-                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false) {
+                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool narrow = false) {
   if (!e.chfsi) return jacobi_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
   e.cw.use_tc = allow_tc;
+  e.cw.narrow = narrow;
   const TBk* Gb = Gb_in;
   if (std::is_same<TBk, double>::value) Gb = reinterpret_cast<const TBk*>(G);
   return eig_topk_chfsi<TBk>(Gb, (int)L, e.k, e.b, d_trace, 1e-6, e.cw, e.w, e.V, stats, st);
@@ -202,6 +203,7 @@ struct SweepInfo {
   double norm = 0;
   int eig_solves = 0;
   int chfsi_products = 0;
+  int fused_filters = 0;  // Chebyshev filters run as one resident kernel (cheb_filter.cuh)
   int tc_grams = 0;
   // TNB_FLAG_PROFILE: CUDA-event timings (ms) on the launching stream, per step (t = 0 is the first Gram)
   int nsteps = 0;
@@ -276,8 +278,9 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   TNB_LAUNCH_CHECK();
   prof.mark(st);
   ChfsiStats cs;
-  TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st, cx.allow_tc));
-  if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products;
+  TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st, cx.allow_tc,
+                       (cx.flags & TNB_FLAG_CONCURRENT) != 0));
+  if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters;
   rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, cx.sc);
   TNB_LAUNCH_CHECK();
   prof.mark(st);

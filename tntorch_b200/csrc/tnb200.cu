@@ -93,7 +93,8 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
     info_host[2] = info.chfsi_products;
     info_host[3] = info.tc_grams;
     info_host[7] = info.nsteps;
-    for (int t = 0; t < info.nsteps && t < 8; ++t) {
+    info_host[31] = info.fused_filters;
+    for (int t = 0; t < info.nsteps && t < 7; ++t) {
       info_host[4] += info.gram_ms[t];
       info_host[5] += info.eig_ms[t];
       info_host[6] += info.factor_ms[t];
@@ -336,6 +337,23 @@ int tnb_atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int64_t
   if (!A || !B || !C || !workspace) return fail(TNB_ERR_INVALID, "tnb_atb_tc_f32: null argument");
   return atb_tc_f32(A, K, m, B, n, C, (int)n, alpha, D, (int)n, beta, nullptr, 0, 0.f, workspace, workspace_bytes,
                     as_stream(stream));
+}
+
+size_t tnb_cheb_filter_workspace_bytes(int32_t n, int32_t b) {
+  if (n < 256 || n % 256 != 0 || b < 8 || b > 128) return 0;
+  return cheb_filter_workspace_bytes(n, b);
+}
+
+int tnb_cheb_filter_f32(const float* G, int32_t n, int32_t b, float* buf0, float* buf1, float* buf2, int32_t steps,
+                        const float* a_host, const float* bc_host, const float* g_host, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  TNB_TRY(require_device());
+  if (!G || !buf0 || !buf1 || !buf2 || !a_host || !bc_host || !g_host || !workspace)
+    return fail(TNB_ERR_INVALID, "tnb_cheb_filter_f32: null argument");
+  float* bufs[3] = {buf0, buf1, buf2};
+  const int rc = cheb_filter_f32(G, n, b, bufs, steps, a_host, bc_host, g_host, workspace, workspace_bytes,
+                                 as_stream(stream));
+  return rc;  // TNB_ERR_UNSUPPORTED carries the reason in tnb_last_error()
 }
 
 int tnb_project(int dtype, const void* A, int64_t rows, int64_t n, const void* V, int32_t r, void* C, void* stream) {

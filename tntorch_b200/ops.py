@@ -70,7 +70,7 @@ def has_tensorcore_path() -> bool:
 
 # --------------------------------------------------------------------------------------
 def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = False, use_tensorcore: bool = True,
-          return_info: bool = False):
+          return_info: bool = False, concurrent: bool = False):
     """Dense tensor -> list of TT cores [r_{k-1}, I_k, r_k] (tn.Tensor(data, ranks_tt=...), tensor.py:401-408)."""
     _require_cuda(data, "ttsvd")
     data = data.contiguous()
@@ -78,7 +78,8 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
     N = data.dim()
     shape = list(data.shape)
     rm = _rmax_list(rmax, max(N - 1, 0))
-    flags = (0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_BATCH_MODE if batch_mode else 0)
+    flags = ((0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_BATCH_MODE if batch_mode else 0) |
+             (_lib.FLAG_CONCURRENT if concurrent else 0))
     L = lib()
     sh = i64(shape)
     rmc = i32(rm) if N > 1 else i32([0])
@@ -101,7 +102,8 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
         r0, r1 = ranks[k], ranks[k + 1]
         cores.append(cores_buf[offs[k]: offs[k] + r0 * shape[k] * r1].view(r0, shape[k], r1))
     if return_info:
-        return cores, dict(norm=info[0], eig_solves=int(info[1]), chfsi_products=int(info[2]), tc_grams=int(info[3]))
+        return cores, dict(norm=info[0], eig_solves=int(info[1]), chfsi_products=int(info[2]), tc_grams=int(info[3]),
+                           fused_filters=int(info[31]))
     return cores
 
 
@@ -109,14 +111,16 @@ class TTSVDPlan:
     """Pre-allocated buffers for repeated decompositions of one shape (bench.py, serving loops)."""
 
     def __init__(self, shape: Sequence[int], dtype: torch.dtype, rmax=None, device="cuda", use_tensorcore: bool = True,
-                 host_io: bool = False, profile: bool = False):
+                 host_io: bool = False, profile: bool = False, concurrent: bool = False):
         self.shape = [int(s) for s in shape]
         self.N = len(self.shape)
         self.dtype = dtype
         self.device = torch.device(device)
         self.code = _DT[dtype]
         self.rm = _rmax_list(rmax, max(self.N - 1, 0))
-        self.flags = (0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_PROFILE if profile else 0)
+        # concurrent: several plans run at once on different streams (TNB_FLAG_CONCURRENT, include/tnb200.h)
+        self.flags = ((0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_PROFILE if profile else 0) |
+                      (_lib.FLAG_CONCURRENT if concurrent else 0))
         L = lib()
         self._sh = i64(self.shape)
         self._rm = i32(self.rm) if self.N > 1 else i32([0])
@@ -363,6 +367,24 @@ def atb_tensorcore(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, D: Opti
         check(L.tnb_atb_tc_f32(_ptr(A), K, m, _ptr(B), n, _ptr(out), float(alpha), _ptr(D), float(beta), _ptr(ws),
                                ws.numel(), _stream()))
     return out
+
+
+def cheb_filter(G: torch.Tensor, Y0: torch.Tensor, a, bc, g) -> torch.Tensor:
+    """len(a) three-term filter products Y_s = a_s G Y_{s-1} + bc_s Y_{s-1} + g_s Y_{s-2} as one resident
+    cluster kernel (csrc/cheb_filter.cuh); fp32 blocks, TF32 products."""
+    _require_cuda(G, "cheb_filter")
+    n, b = Y0.shape
+    steps = len(a)
+    bufs = [Y0.contiguous().clone(), torch.empty_like(Y0), torch.empty_like(Y0)]
+    wsb = lib().tnb_cheb_filter_workspace_bytes(n, b)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, G.device)
+    fa, fb, fg = ((C.c_float * steps)(*[float(v) for v in x]) for x in (a, bc, g))
+    with torch.cuda.device(G.device):
+        check(lib().tnb_cheb_filter_f32(_ptr(G.contiguous()), n, b, _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), steps,
+                                        fa, fb, fg, _ptr(ws), ws.numel(), _stream()))
+    return bufs[steps % 3]
 
 
 def project(A: torch.Tensor, V: torch.Tensor, tensorcore: bool = False) -> torch.Tensor:
