@@ -3,19 +3,22 @@
 // i.e. the accuracy class of an fp32 FFMA product — a plain TF32 projection would put a 2^-11 relative error
 // straight into the reconstruction).  This is the "C <- C V_r" step of the sweep (round.py:181, tensor.py:2081-2083).
 //
-//   * A row blocks (128 rows x 32 k) are staged by TMA (K-major, SWIZZLE_128B), 6-stage mbarrier ring; the matching
-//     V_hi^T / V_lo^T chunks (r x 32 k) ride in the same stage, stacked as ONE B operand of 2*r_pad rows;
-//   * the tensor core truncates fp32 operands to TF32 itself, so A_hi is the raw tile: one SS MMA
-//     A x [V_hi; V_lo] (N = 2*r_pad) gives A_hi V_hi and A_hi V_lo side by side in TMEM;
-//   * A_lo = A - trunc(A) is produced by four "split" warps (thread = row, conflict-free reads of the swizzled
-//     tile) and written to TENSOR MEMORY (tcgen05.st), from where a TS MMA (A operand in TMEM) adds A_lo V_hi
-//     onto the first r_pad accumulator columns — the tile crosses the shared-memory port three times (TMA fill,
-//     split read, MMA read) instead of six;
+//   * A row blocks (128 rows x 32 k) are staged by TMA (K-major, SWIZZLE_128B) into a deep mbarrier ring (11 x 16 KB
+//     when V fits in shared memory, else 8 x 24 KB with the V chunk riding in the stage); V_hi^T / V_lo^T are stacked
+//     as ONE B operand of 2*r_pad rows;
+//   * four "split" warps (thread = row, conflict-free reads of the swizzled tile) put BOTH the raw tile and
+//     A_lo = A - trunc(A) into TENSOR MEMORY (tcgen05.st); every MMA then takes its A operand from TMEM (TS form):
+//     A_raw x [V_hi; V_lo] (N = 2*r_pad; the tensor core truncates the raw bits to TF32 itself, so this is
+//     A_hi V_hi | A_hi V_lo side by side) and A_lo x V_hi (N = r_pad) onto the first r_pad accumulator columns.
+//     The tile crosses the shared-memory port twice (TMA fill, split read) instead of six times;
 //   * four epilogue warps drain finished tiles (tcgen05.ld), add the two halves and store, while the next row
 //     block is already being multiplied (persistent CTAs, static round-robin over row blocks).
 //
-// Bound: HBM (reads A once: 4 B/element for 2*r flop) — the MMAs cost 3*128*r*8 MACs per 128x8 elements, far
-// below the tensor-pipe limit; the shared-memory port (68 KB moved per 16 KB tile) stays below the HBM feed.
+// What bounds it (measured, profiles/r01_ncu_summaries.md): a tcgen05.mma of M=128, K=8 occupies the tensor pipe for
+// ~100 (TS) to ~140 (SS) cycles however small N is, and one thread issues all of them, so the MMA-issuing thread
+// paces the CTA: 8 instructions per 16 KB chunk.  With all-TS operands and no integer divisions in that thread's
+// loop the chunk time drops below the HBM feed for K = 64 (5.76 TB/s = 88 % of the measured copy peak); for
+// K = 2048 the 8 KB row pitch leaves 256-byte DRAM bursts per page and the kernel stays at ~4.4 TB/s.
 #pragma once
 #include "gram_tc.cuh"
 
@@ -29,7 +32,8 @@ constexpr int PT_SMEM_BYTES = PT_RING_BYTES + 1024 + 512;
 constexpr int PT_VRES_MAX_BYTES = 32 * 1024;        // V_hi|V_lo kept in shared memory for the whole kernel up to this size
 constexpr int PT_ACC_COLS = 256;                    // accumulator slots: 256 / (2*npad) of width 2*npad
 constexpr int PT_ALO_COL = PT_ACC_COLS;             // A_lo ring: PT_ALO_SLOTS x 32 columns behind the accumulators
-constexpr int PT_ALO_SLOTS = 8;  // 8 x 32 columns: with the 256 accumulator columns exactly the 512 of an SM
+constexpr int PT_ALO_SLOTS = 4;  // 4 x (32 raw + 32 lo) columns: with the 256 accumulator columns exactly the 512 of an SM
+constexpr int PT_ALO_W = 2 * PT_KC;
 constexpr int PT_TMEM_COLS = 512;
 constexpr int PT_MAX_SLOTS = 8;
 
@@ -199,17 +203,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           const uint32_t sb = stage0 + (uint32_t)(stage * p.stage_bytes);
           const uint32_t vb = p.vres ? vres0 + (uint32_t)(kc * vchunk_bytes) : sb + PT_A_BYTES;
-          const uint64_t ad = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF), bd = desc_hi | (uint64_t)((vb >> 4) & 0x3FFF);
-          const uint32_t alo = tmem_base + (uint32_t)(PT_ALO_COL + aslot * PT_KC);
-          mbar_wait(&full_bar[stage], phase);
+          const uint64_t bd = desc_hi | (uint64_t)((vb >> 4) & 0x3FFF);
+          const uint32_t araw = tmem_base + (uint32_t)(PT_ALO_COL + aslot * PT_ALO_W), alo = araw + PT_KC;
+          mbar_wait(&full_bar[stage], phase);   // V chunk of this stage (streaming mode) landed
+          mbar_wait(&alo_full[aslot], aphase);  // the split warps have put A (raw) and A_lo of this chunk in tensor memory
           tcgen05_fence_after();
-          // A_hi (raw, truncated by the tensor core) x [V_hi; V_lo]; one k-step = 32 B = +2 in the address field
-          tcgen05_mma_tf32(tmem_d, ad, bd, idesc2, kc > kc_begin ? 1u : 0u);
-          tcgen05_mma_tf32(tmem_d, ad + 2, bd + 2, idesc2, 1u);
-          tcgen05_mma_tf32(tmem_d, ad + 4, bd + 4, idesc2, 1u);
-          tcgen05_mma_tf32(tmem_d, ad + 6, bd + 6, idesc2, 1u);
-          mbar_wait(&alo_full[aslot], aphase);  // A_lo of this chunk is in tensor memory
-          tcgen05_fence_after();
+          // A_hi (raw bits, truncated by the tensor core) x [V_hi; V_lo]; one k-step = 8 TMEM columns / 32 B of V
+          tcgen05_mma_tf32_ts(tmem_d, araw, bd, idesc2, kc > kc_begin ? 1u : 0u);
+          tcgen05_mma_tf32_ts(tmem_d, araw + 8, bd + 2, idesc2, 1u);
+          tcgen05_mma_tf32_ts(tmem_d, araw + 16, bd + 4, idesc2, 1u);
+          tcgen05_mma_tf32_ts(tmem_d, araw + 24, bd + 6, idesc2, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo, bd, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 8, bd + 2, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 16, bd + 4, idesc1, 1u);
@@ -234,18 +237,24 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int64_t item = 0; item < total_items; ++item) {
       mbar_wait(&full_bar[stage], phase);
       const unsigned char* a = stage_base + (size_t)stage * p.stage_bytes + row_off;
-      uint32_t lo[32];
+      uint32_t raw[32], lo[32];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {  // 16-byte unit u of the row sits at (u ^ (row % 8)) under SWIZZLE_128B
         const float4 v = *reinterpret_cast<const float4*>(a + ((u ^ (m & 7)) << 4));
+        raw[4 * u + 0] = __float_as_uint(v.x);
+        raw[4 * u + 1] = __float_as_uint(v.y);
+        raw[4 * u + 2] = __float_as_uint(v.z);
+        raw[4 * u + 3] = __float_as_uint(v.w);
         lo[4 * u + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
         lo[4 * u + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
         lo[4 * u + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
         lo[4 * u + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
       }
-      mbar_wait(&alo_empty[aslot], aphase ^ 1u);  // the TS MMA that read this slot last has completed
+      mbar_wait(&alo_empty[aslot], aphase ^ 1u);  // the MMAs that read this slot last have completed
       tcgen05_fence_after();
-      tmem_st_32x32b_x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(PT_ALO_COL + aslot * PT_KC), lo);
+      const uint32_t tdst = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(PT_ALO_COL + aslot * PT_ALO_W);
+      tmem_st_32x32b_x32(tdst, raw);
+      tmem_st_32x32b_x32(tdst + PT_KC, lo);
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
