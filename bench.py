@@ -35,9 +35,11 @@ def parse():
     ap.add_argument("--no-tc", action="store_true", help="generic CUDA-core kernels only (A/B runs)")
     ap.add_argument("--cpu-shape", default="32,32,32,32,32", help="bounded sample timed on the host cores")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (measured: no gain on B200, default 0)")
-    ap.add_argument("--per-gpu-batch", type=int, default=4,
+    ap.add_argument("--per-gpu-batch", type=int, default=6,
                     help="independent tensors decomposed concurrently per GPU (one CUDA stream + host thread each): the "
                          "latency-bound eigen phases of one overlap the bandwidth-bound Gram/projection phases of another")
+    ap.add_argument("--step-barrier", action="store_true",
+                    help="join all in-flight tensors after every step instead of once after the K steps")
     ap.add_argument("--no-concurrent-flag", action="store_true",
                     help="A/B: do not pass TNB_FLAG_CONCURRENT when several tensors are in flight")
     return ap.parse_args()
@@ -216,14 +218,16 @@ def run_ours(args):
     bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
 
     PB = max(1, args.per_gpu_batch)
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else 0
+    concurrent = PB > 1 and not args.no_concurrent_flag
+    # concurrent mode: gram_tc2 already leaves 4 SMs idle (72 CTA pairs); keep the same 4 free in every whole-GPU kernel
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (4 if concurrent else 0)
     ops.set_reserved_sms(reserve)
     Xs, plans, streams = [], [], []
     for b in range(PB):
         g = torch.Generator(device=dev).manual_seed(1234 + rank_id * 16 + b)
         Xs.append(torch.randn(shape, generator=g, device=dev, dtype=torch.float32))  # 4 GiB each >> 126 MB L2
         plans.append(ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc,
-                                   concurrent=(PB > 1 and not args.no_concurrent_flag)))
+                                   concurrent=concurrent))
         streams.append(torch.cuda.Stream(device=dev))
     X, plan = Xs[0], plans[0]
     prof_plan = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, profile=True)
@@ -242,23 +246,37 @@ def run_ours(args):
         out = torch.empty(world * flat.numel(), dtype=flat.dtype, device=dev)
         dist.all_gather_into_tensor(out, flat)  # the final factor broadcast (north_star)
 
-    def run_one(b):
+    def run_many(b, k):
+        """Worker b: k decompositions back to back on its own stream (no barrier between steps)."""
         torch.cuda.set_device(local)
         with torch.cuda.stream(streams[b]):
-            return plans[b].run(Xs[b])
+            for _ in range(k):
+                cores = plans[b].run(Xs[b])
+        return cores
 
-    def step():
+    def run_steps(k):
+        """k steps = k * PB decompositions.  With several tensors in flight the workers stream through their k
+        tensors independently (a step boundary is not a barrier: the eigen chain that ends one tensor overlaps the
+        Gram of the next), joined once at the end; --step-barrier restores a join after every step."""
         if PB == 1:
-            cores_list = [plan.run(X)]
-        else:
-            cur = torch.cuda.current_stream()
+            for _ in range(k):
+                cores_list = [plan.run(X)]
+                gather_cores(cores_list)
+            return cores_list[0]
+        cur = torch.cuda.current_stream()
+        rounds = [1] * k if args.step_barrier else [k]
+        for kk in rounds:
             for sb in streams:
                 sb.wait_stream(cur)
-            cores_list = list(pool.map(run_one, range(PB)))  # one host thread per in-flight tensor
+            cores_list = list(pool.map(lambda b: run_many(b, kk), range(PB)))  # one host thread per in-flight tensor
             for sb in streams:
                 cur.wait_stream(sb)
-        gather_cores(cores_list)
+            for _ in range(kk):  # the final-factor all-gather of each step (the plan buffers hold the last step's cores)
+                gather_cores(cores_list)
         return cores_list[0]
+
+    def step():
+        return run_steps(1)
 
     def barrier():
         if world > 1:
@@ -276,8 +294,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        cores = step()
+    cores = run_steps(args.steps)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -433,6 +450,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"TT-SVD randn{list(shape)} fp32 -> TT-rank {args.rank} (stand-in for the infeasible 64^8: 1.1 PB)",
                        "per_gpu_batch": PB, "in_flight_per_gpu": PB, "reserved_sms": reserve,
+                       "step_join": "every step" if (args.step_barrier or PB == 1) else "once after the K steps (workers stream)",
+                       "concurrent_flag": bool(concurrent),
                        "parallelism": f"batch-sharded x{world} ({PB} independent tensors in flight per GPU on {PB} streams), all-gather of final cores",
                        "l2": "input 4 GiB >> 126 MB L2 (no flush needed)", "ranks": ranks},
             "rel_error": relerr,

@@ -42,8 +42,9 @@ extern "C" {
 #define TNB_FLAG_BATCH_MODE 2u    /* reference `batch=True` rank rule: rank = min(rmax, len(S)), no eps  */
 #define TNB_FLAG_PROFILE 4u       /* record CUDA events around each phase; timings returned in info_host  */
 #define TNB_FLAG_CONCURRENT 8u    /* the caller runs several decompositions at once on different streams: the
-                                    latency-bound eigen-iteration kernels then use few SMs (one CTA per output
-                                    tile) instead of the whole GPU, leaving the rest to the other streams   */
+                                    whole-GPU kernels (tensor-core Gram, projection) of all of them are chained
+                                    one at a time and sized to leave tnb_set_reserved_sms() SMs free for the
+                                    one-CTA eigen kernels of the others                                       */
 
 int tnb_version(void);
 const char* tnb_last_error(void);

@@ -125,9 +125,11 @@ def test_sweep_uses_resident_filter():
 
 
 @pytest.mark.parametrize("name", ["twin32x5_r32_f32", "randn64x4_r32_f32"])
-def test_concurrent_flag_same_result(name):
-    """TNB_FLAG_CONCURRENT only changes how the eigen-iteration products are scheduled (one CTA per output
-    tile, direct epilogue): ranks and error must match the golden vectors just the same."""
+@pytest.mark.parametrize("narrow", [False, True])
+def test_concurrent_flag_same_result(name, narrow, monkeypatch):
+    """TNB_FLAG_CONCURRENT only changes scheduling (whole-GPU kernels chained across streams and sized to leave
+    the reserved SMs free, no resident filter kernel): ranks and error must match the golden vectors just the same.
+    TNB_NARROW additionally routes the filter products through the one-CTA-per-tile direct-epilogue form."""
     import os
 
     import numpy as np
@@ -135,6 +137,8 @@ def test_concurrent_flag_same_result(name):
     from oracle import cases
     from tntorch_b200 import ops
 
+    if narrow:
+        monkeypatch.setenv("TNB_NARROW", "1")
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ttsvd.npz"))
     spec = cases.TTSVD_CASES[name]
     X = cases.make_dense(spec)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -132,6 +133,33 @@ inline int usable_sms() {
   if (r > sms - 8) r = sms - 8;
   return sms - r;
 }
+
+// TNB_FLAG_CONCURRENT: the bandwidth-bound whole-GPU kernels (tensor-core Gram, projection) of the decompositions in
+// flight are chained across their streams, one at a time, each sized to usable_sms(): the reserved SMs then stay free
+// for the latency-bound eigen chains of the OTHER decompositions (one-CTA Jacobi / Cholesky kernels, narrow
+// products), which would otherwise queue behind — or steal an SM from and double the time of — a one-wave kernel.
+class BigKernelGate {
+ public:
+  BigKernelGate(cudaStream_t st, bool enabled) : st_(st), on_(enabled) {
+    if (!on_) return;
+    mu().lock();
+    if (!ev()) cudaEventCreateWithFlags(&ev(), cudaEventDisableTiming);
+    cudaStreamWaitEvent(st_, ev(), 0);
+  }
+  ~BigKernelGate() {
+    if (!on_) return;
+    cudaEventRecord(ev(), st_);
+    mu().unlock();
+  }
+  BigKernelGate(const BigKernelGate&) = delete;
+  BigKernelGate& operator=(const BigKernelGate&) = delete;
+
+ private:
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static cudaEvent_t& ev() { static cudaEvent_t e = nullptr; return e; }
+  cudaStream_t st_;
+  bool on_;
+};
 
 // Pinned host scratch for reading small results back (ranks, Ritz values).
 inline void* pinned_scratch(size_t bytes) {

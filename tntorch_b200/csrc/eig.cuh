@@ -37,7 +37,8 @@ struct ChfsiWork {
   void* partial;            // split-K scratch, partial_bytes
   size_t partial_bytes;
   bool use_tc = false;      // filter products on the tcgen05 kernel (fp32 blocks only)
-  bool narrow = false;      // TNB_FLAG_CONCURRENT: products on one CTA per output tile, no resident whole-GPU filter
+  bool narrow = false;      // products on one CTA per output tile with a direct epilogue (opt-in, TNB_NARROW; measured slower)
+  bool shared_gpu = false;  // TNB_FLAG_CONCURRENT: other decompositions run beside this one: no resident 128-SM filter kernel
   double *S, *lam, *Q, *d;  // b*b, b, b*b, b
   double* jscratch;         // jacobi_scratch_doubles(b)
   int* jinfo;
@@ -221,7 +222,8 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
         if (all3[q] != X) bufs[c3++] = all3[q];
     }
     bool fused = false;
-    if (w.use_tc && !w.narrow && std::is_same<TB, float>::value && m <= CF_MAX_STEPS) {
+    if (w.use_tc && !w.narrow && !w.shared_gpu && std::is_same<TB, float>::value && m <= CF_MAX_STEPS &&
+        !getenv("TNB_NO_RESIDENT_FILTER")) {
       // the whole filter as one resident kernel (cheb_filter.cuh); same recurrence, coefficients precomputed
       float fa[CF_MAX_STEPS], fb[CF_MAX_STEPS], fg[CF_MAX_STEPS];
       double sg = sigma1;

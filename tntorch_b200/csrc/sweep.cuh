@@ -184,10 +184,11 @@ inline int eig_carve(ArenaT& ar, int64_t L, int64_t rcap, bool have_rmax, EigWor
 
 template <typename TBk>
 inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e, const double* d_trace,
-                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool narrow = false) {
+                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool shared_gpu = false) {
   if (!e.chfsi) return jacobi_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
   e.cw.use_tc = allow_tc;
-  e.cw.narrow = narrow;
+  e.cw.shared_gpu = shared_gpu;
+  e.cw.narrow = shared_gpu && getenv("TNB_NARROW") != nullptr;
   const TBk* Gb = Gb_in;
   if (std::is_same<TBk, double>::value) Gb = reinterpret_cast<const TBk*>(G);
   return eig_topk_chfsi<TBk>(Gb, (int)L, e.k, e.b, d_trace, 1e-6, e.cw, e.w, e.V, stats, st);
@@ -272,14 +273,18 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   Prof& prof = Prof::get();
   prof.mark(st);
   int used_tc = 0;
-  TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, cx.allow_tc, &used_tc, st));
+  const bool concurrent = (cx.flags & TNB_FLAG_CONCURRENT) != 0;
+  {
+    BigKernelGate gate(st, concurrent && gw.tc_ws != nullptr);
+    TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, cx.allow_tc, &used_tc, st));
+  }
   if (cx.info) cx.info->tc_grams += used_tc;
   trace_kernel<<<1, 256, 0, st>>>(G, (int)L, (int)L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
   TNB_LAUNCH_CHECK();
   prof.mark(st);
   ChfsiStats cs;
   TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st, cx.allow_tc,
-                       (cx.flags & TNB_FLAG_CONCURRENT) != 0));
+                       concurrent));
   if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters;
   rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, cx.sc);
   TNB_LAUNCH_CHECK();
@@ -302,7 +307,10 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
     TNB_LAUNCH_CHECK();
     scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)n, (int)rank, ew.w, fac, 0, 0);
     TNB_LAUNCH_CHECK();
-    TNB_TRY(project_any<T>(C, rows, n, fac, rank, Cn, st, ptc_ws, ptc_bytes));
+    {
+      BigKernelGate gate(st, concurrent && rows >= PROJ_TC_MIN_ROWS);
+      TNB_TRY(project_any<T>(C, rows, n, fac, rank, Cn, st, ptc_ws, ptc_bytes));
+    }
   } else {
     // core = diag(1/s) U_r^T C (rank x n);  Cn = U_r diag(s)
     scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(ew.V, ew.ldv, (int)rows, (int)rank, ew.w, fac, 1, 0);
