@@ -366,11 +366,23 @@ def run_ours(args):
     # (profiles/r01_ncu_summaries.md) for the default 64^5 / r=32 workload; null for other shapes
     roof["traffic"] = None
     if list(shape) == [64] * 5 and args.rank == 32 and not args.no_tc:
-        ncu_traffic = {("gram", 0): 4.295e9 + 0.004e9, ("factor", 0): 4.297e9 + 2.15e9, ("gram", 1): 4.937e9 + 0.02e9}
+        ncu_traffic = {("gram", 0): 4.295e9 + 0.004e9, ("factor", 0): 4.296e9 + 2.109e9, ("gram", 1): 4.185e9 + 0.008e9}
         roof["traffic"] = ncu_traffic.get((top_kind, top_s))
         roof["traffic_source"] = "profiles/r01_ncu_summaries.md (ncu --set full, per launch)"
     roof["ms"] = top_ms
     roof["peak_source"] = peak_src
+    # the other single-kernel phases against their own bound (same CUDA-event timings), largest first
+    others = []
+    for ms_k, name_k, s_k, kind_k in cand[:4]:
+        rws_k, cls_k, rr_k = dims[s_k]
+        if kind_k == "gram" and cls_k > 512:
+            others.append({"kernel": "gram_tc2_kernel " + name_k, "ms": ms_k, "bound": "tensor",
+                           "frac": rws_k * cls_k * (cls_k + 1) / ms_k / 1e9 / (bf16_sus / 2)})
+        else:
+            by_k = rws_k * cls_k * 4 + (rws_k * rr_k * 4 if kind_k == "factor" else 0)
+            others.append({"kernel": ("gram_tc_kernel " if kind_k == "gram" else "") + name_k, "ms": ms_k, "bound": "hbm",
+                           "frac": by_k / ms_k / 1e6 / hbm_peak})
+    roof["kernels"] = others
     sweep_roof = {"alg_bytes_per_tensor": B_alg, "achieved_GBps": PB * B_alg / ms_step / 1e6, "peak_GBps": hbm_peak,
                   "frac": PB * B_alg / ms_step / 1e6 / hbm_peak}
 

@@ -7,4 +7,4 @@ timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 900 python bench.py --per-gpu-batch 1 > gpurun_out/bench_pb1.json 2> gpurun_out/bench_pb1.err; echo "bench pb1 rc=$?"; cut -c1-300 gpurun_out/bench_pb1.json
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-900 gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --per-gpu-batch 1 > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gram_tc2_kernel|gram_tc_kernel|project_tc_kernel" -c 4 -o gpurun_out/prof_tc python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --per-gpu-batch 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gram_tc2_kernel|gram_tc_kernel|project_tc_kernel|cheb_filter_kernel" -c 6 -o gpurun_out/prof_tc python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --per-gpu-batch 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
