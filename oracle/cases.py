@@ -126,6 +126,10 @@ TTSVD_CASES = {
     "eps_twin_f64": dict(kind="tt_noise", shape=(12, 10, 8, 9, 7), rank=4, noise=1e-6, seed=7, dtype="float64", eps=1e-4),
     "eps_smooth_f64": dict(kind="smooth", shape=(20, 18, 16, 14), dtype="float64", eps=1e-6),
     "smooth_f32_r6": dict(kind="smooth", shape=(20, 18, 16, 14), dtype="float32", ranks_tt=6),
+    # eps-only with a Gram matrix larger than the direct eigensolver (step 1: 320 / 288 columns): the leading values
+    # come from the subspace iteration in growing blocks until the tail-energy rule is decided
+    "eps_biggram_f32": dict(kind="tt_noise", shape=(40,) * 4, rank=8, noise=1e-3, seed=12, dtype="float32", eps=2e-2, big=True),
+    "eps_biggram_f64": dict(kind="tt_noise", shape=(24,) * 4, rank=12, noise=1e-6, seed=13, dtype="float64", eps=1e-4),
     # tutorial known answers (docs/tutorials/decompositions.ipynb:68,361)
     "analytic128_r3": dict(kind="analytic128", dtype="float64", ranks_tt=3, big=False),
     "analytic128_eps": dict(kind="analytic128", dtype="float64", eps=1e-5, big=False),
@@ -154,6 +158,7 @@ TSVD_CASES = {
     "lowrank_60x80": dict(shape=(60, 80), seed=33, lowrank=6, noise=1e-9, eps=1e-6),
     "zero_10x7": dict(shape=(10, 7), seed=34, zero=True, rmax=3),
     "f32_64x128_rmax": dict(shape=(64, 128), seed=35, rmax=16, dtype="float32"),
+    "lowrank_600x500_eps": dict(shape=(600, 500), seed=36, lowrank=20, noise=1e-6, eps=1e-4),
 }
 
 # ---- maxvol ---------------------------------------------------------------------------

@@ -147,3 +147,40 @@ def test_concurrent_flag_same_result(name, narrow, monkeypatch):
     assert ranks_of(cores) == list(g[f"{name}/{alg}/ranks"])
     assert abs(relerr64(X, cores) - float(g[f"{name}/{alg}/relerr"])) <= 1e-5
     assert info["fused_filters"] == 0
+
+
+def test_concurrent_threads_match_golden():
+    """Three decompositions in flight on three streams / host threads with TNB_FLAG_CONCURRENT (the bench's
+    schedule: event-chained whole-GPU kernels, reserved SMs): every one must still match the golden vectors."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    from gpu_util import ranks_of, relerr64
+    from oracle import cases
+    from tntorch_b200 import ops
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ttsvd.npz"))
+    names = ["twin32x5_r32_f32", "randn64x4_r32_f32", "randn32x5_r32_f32"]
+    Xs = [cases.make_dense(cases.TTSVD_CASES[n]) for n in names]
+    Xd = [torch.as_tensor(x).cuda() for x in Xs]
+    streams = [torch.cuda.Stream() for _ in names]
+    ops.set_reserved_sms(4)
+    try:
+        def run(i):
+            torch.cuda.set_device(0)
+            out = None
+            with torch.cuda.stream(streams[i]):
+                for _ in range(3):
+                    out = ops.ttsvd(Xd[i], rmax=cases.TTSVD_CASES[names[i]]["ranks_tt"], concurrent=True)
+                streams[i].synchronize()
+            return out
+
+        with ThreadPoolExecutor(len(names)) as pool:
+            res = list(pool.map(run, range(len(names))))
+    finally:
+        ops.set_reserved_sms(0)
+    for n, x, cores in zip(names, Xs, res):
+        alg = "svd" if f"{n}/svd/relerr" in g.files else "eig"
+        assert ranks_of(cores) == list(g[f"{n}/{alg}/ranks"])
+        assert abs(relerr64(x, cores) - float(g[f"{n}/{alg}/relerr"])) <= 1e-5

@@ -50,6 +50,8 @@ def test_tutorial_known_answers():
 @pytest.mark.parametrize("name", list(cases.ROUND_CASES))
 @pytest.mark.parametrize("alg", ["svd", "eig"])
 def test_round_tt_oracle_matches_reference(name, alg):
+    if alg == "svd" and name == "cfg3_small_f64":
+        pytest.skip("the 'svd' variant forms a 32768 x 32768 Vh per step only to discard it (2 min); 'eig' covers the case")
     g = _g("round_tt.npz")
     spec = cases.ROUND_CASES[name]
     cores = cases.make_tt(spec)

@@ -285,6 +285,13 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
     stats->outer += outer;
     stats->converged = converged ? 1 : 0;
   }
+  if (!use_chol) {
+    // a Cholesky breakdown was seen (numerically rank-deficient block, e.g. an exactly low-rank input): the
+    // eigen-decomposition based transform clamps the lost directions, which leaves the Ritz vectors orthonormal
+    // only to ~1e-5.  One Cholesky-QR pass in column order (= Gram-Schmidt: the leading, well-conditioned vectors
+    // are untouched by the clamped trailing pivots) restores them to working precision.
+    TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st, true));
+  }
   TNB_CUDA(cudaMemcpyAsync(theta_out, w.lam, (size_t)b * sizeof(double), cudaMemcpyDeviceToDevice, st));
   convert_kernel<TB, double><<<grid_for((int64_t)n * b), 256, 0, st>>>(X, X_out, (int64_t)n * b);
   TNB_LAUNCH_CHECK();

@@ -244,12 +244,8 @@ inline int truncated_svd_impl(ArenaT& ar, bool dry, const T* M, int64_t m, int64
   TNB_LAUNCH_CHECK();
   set_delta2_kernel<<<1, 32, 0, st>>>(sc, delta, eps);
   TNB_LAUNCH_CHECK();
-  ChfsiStats cs;
-  TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &sc->trace, &cs, st));
-  rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rmax, ew.chfsi ? 1 : 0, 0, sc);
-  TNB_LAUNCH_CHECK();
-  TNB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
-  TNB_CUDA(cudaStreamSynchronize(st));
+  TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, sc, h_sc, rmax, 0, nullptr, nullptr, st, false,
+                                  false));
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(h_sc);
   int64_t r = std::min<int64_t>(hs->rank, kcap);
   if (hs->zero_flag) {  // round.py:137-145

@@ -14,7 +14,8 @@ struct SweepScalars {
   int rank;          // chosen rank of the current step
   int zero_flag;     // 1 when the current unfolding is numerically zero (round.py:137-145)
   int jacobi_info;   // sweeps used by the last Jacobi solve (negative: not converged)
-  int spare_i[5];
+  int undecided;     // leading-values rule only: 1 when the tail behind the kk known values is still above delta^2
+  int spare_i[4];
 };
 
 __global__ void trace_kernel(const double* __restrict__ G, int n, int ld, SweepScalars* sc, int set_norm,
@@ -50,6 +51,7 @@ __global__ void rank_rule_kernel(const double* __restrict__ w, int L, int kk, in
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double w0 = w[0] > 0.0 ? w[0] : 0.0;
   sc->zero_flag = (sqrt(w0) < 1e-13) ? 1 : 0;
+  sc->undecided = 0;
   int cap = L;
   if (rmax > 0 && rmax < cap) cap = rmax;
   int rank;
@@ -69,11 +71,13 @@ __global__ void rank_rule_kernel(const double* __restrict__ w, int L, int kk, in
     // rank = min(cap, L - count_true); only ranks <= cap matter, and tail_k for k < cap is computable
     double head = 0.0;
     rank = cap;
+    sc->undecided = (cap > kk) ? 1 : 0;  // cleared when a rank within the known values meets the budget
     for (int k = 0; k < cap && k < kk; ++k) {
       head += (w[k] > 0.0 ? w[k] : 0.0);
       const double tail = sc->trace - head;  // energy discarded if the rank were k+1
       if (tail <= sc->delta2) {
         rank = k + 1;
+        sc->undecided = 0;
         break;
       }
     }

@@ -147,7 +147,9 @@ struct EigWork {
   double* jscratch = nullptr;
   int* jinfo = nullptr;
   bool chfsi = false;
-  int k = 0, b = 0;
+  bool adaptive = false;  // eps-only: k grows until the rank rule is decided
+  int k = 0, b = 0;       // capacity (carved); k_run / b_run are what the last solve used
+  int k_run = 0, b_run = 0;
   TBk* Gb = nullptr;  // G in block precision (ChFSI only)
   ChfsiWork<TBk> cw;
 };
@@ -163,13 +165,14 @@ inline int eig_carve(ArenaT& ar, int64_t L, int64_t rcap, bool have_rmax, EigWor
     e.jinfo = ar.template take<int>(4);
     return TNB_OK;
   }
-  if (!have_rmax)
-    return fail(TNB_ERR_UNSUPPORTED,
-                "eps-only truncation needs the full spectrum of a %lld x %lld Gram matrix; pass rmax / ranks_tt "
-                "(direct eigensolver limit is %d)", (long long)L, (long long)L, JACOBI_MAX_N);
-  if (rcap + 16 > JACOBI_MAX_N)
+  // eps-only truncation (no rank cap) of a large Gram matrix: the leading values are computed in growing blocks
+  // (k = 32, 64, 128, 240) until the tail-energy rule is decided; ranks above 240 are out of reach of the subspace
+  // eigensolver and raise.
+  e.adaptive = !have_rmax;
+  if (have_rmax && rcap + 16 > JACOBI_MAX_N)
     return fail(TNB_ERR_UNSUPPORTED, "target rank %lld too large for the subspace eigensolver (limit %d) at Gram size %lld",
                 (long long)rcap, JACOBI_MAX_N - 16, (long long)L);
+  if (!have_rmax || rcap + 16 > JACOBI_MAX_N) rcap = JACOBI_MAX_N - 16;
   if (L > 46000) return fail(TNB_ERR_UNSUPPORTED, "Gram size %lld too large", (long long)L);
   e.chfsi = true;
   e.k = (int)rcap;
@@ -184,14 +187,54 @@ inline int eig_carve(ArenaT& ar, int64_t L, int64_t rcap, bool have_rmax, EigWor
 
 template <typename TBk>
 inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e, const double* d_trace,
-                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool shared_gpu = false) {
+                   ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool shared_gpu = false, int k_try = 0,
+                   double tol = 1e-6) {
   if (!e.chfsi) return jacobi_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
   e.cw.use_tc = allow_tc;
   e.cw.shared_gpu = shared_gpu;
   e.cw.narrow = shared_gpu && getenv("TNB_NARROW") != nullptr;
+  e.k_run = (k_try > 0 && k_try < e.k) ? k_try : e.k;
+  e.b_run = chfsi_default_block((int)L, e.k_run);
+  if (e.b_run > e.b) e.b_run = e.b;
+  e.ldv = e.b_run;
   const TBk* Gb = Gb_in;
   if (std::is_same<TBk, double>::value) Gb = reinterpret_cast<const TBk*>(G);
-  return eig_topk_chfsi<TBk>(Gb, (int)L, e.k, e.b, d_trace, 1e-6, e.cw, e.w, e.V, stats, st);
+  return eig_topk_chfsi<TBk>(Gb, (int)L, e.k_run, e.b_run, d_trace, tol, e.cw, e.w, e.V, stats, st);
+}
+
+// Eigen stage + rank rule + host read-back of the step scalars (one sync, which the caller needs anyway for the rank).
+// eps-only truncation of a large Gram matrix (EigWork::adaptive) repeats the subspace solve with k = 32, 64, 128, 240
+// leading values until the tail-energy rule is decided, with a stopping rule fine enough to resolve delta^2.
+template <typename TBk>
+inline int eig_solve_and_rank(const double* G, const TBk* Gb, int64_t L, EigWork<TBk>& ew, SweepScalars* sc, int* h_sc,
+                              int32_t rm, int batch_mode, ChfsiStats* total, int* solves, cudaStream_t st, bool allow_tc,
+                              bool shared_gpu) {
+  const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(h_sc);
+  const bool adaptive = ew.chfsi && ew.adaptive;
+  int k_try = adaptive ? 32 : 0;
+  double tol = 1e-6;
+  if (adaptive) {
+    TNB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(cudaStreamSynchronize(st));
+    const double floor_tol = std::is_same<TBk, float>::value ? 3e-8 : 1e-12;
+    if (hs->trace > 0.0) tol = std::min(1e-6, std::max(floor_tol, 0.05 * hs->delta2 / hs->trace));
+  }
+  for (;;) {
+    ChfsiStats cs;
+    TNB_TRY(eig_run<TBk>(G, Gb, L, ew, &sc->trace, &cs, st, allow_tc, shared_gpu, k_try, tol));
+    if (total) total->products += cs.products, total->fused_filters += cs.fused_filters, total->outer += cs.outer;
+    if (solves) *solves += 1;
+    rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.k_run : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, sc);
+    TNB_LAUNCH_CHECK();
+    TNB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(cudaStreamSynchronize(st));
+    if (!adaptive || !hs->undecided || hs->zero_flag) return TNB_OK;
+    if (ew.k_run >= ew.k)
+      return fail(TNB_ERR_UNSUPPORTED,
+                  "eps-only truncation of a %lld x %lld Gram matrix needs a rank above %d; pass rmax / ranks_tt "
+                  "(the direct eigensolver stops at %d)", (long long)L, (long long)L, ew.k, JACOBI_MAX_N);
+    k_try = 2 * ew.k_run > 128 ? ew.k : 2 * ew.k_run;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -283,14 +326,11 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   TNB_LAUNCH_CHECK();
   prof.mark(st);
   ChfsiStats cs;
-  TNB_TRY(eig_run<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, &cx.sc->trace, &cs, st, cx.allow_tc,
-                       concurrent));
-  if (cx.info) cx.info->eig_solves += 1, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters;
-  rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.b : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, cx.sc);
-  TNB_LAUNCH_CHECK();
+  int solves = 0;
+  TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, cx.sc, cx.h_sc, rm, batch_mode, &cs, &solves, st,
+                                  cx.allow_tc, concurrent));
+  if (cx.info) cx.info->eig_solves += solves, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters;
   prof.mark(st);
-  TNB_CUDA(cudaMemcpyAsync(cx.h_sc, cx.sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
-  TNB_CUDA(cudaStreamSynchronize(st));
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(cx.h_sc);
   if (first_step && cx.info) cx.info->norm = std::sqrt(hs->norm2 > 0 ? hs->norm2 : 0.0);
   int64_t rank = hs->rank;

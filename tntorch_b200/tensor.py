@@ -88,19 +88,29 @@ class Tensor(object):
                         ops.cp_als(data[b], ranks_cp, max_iter=max_iter, tol=tol) for b in range(data.shape[0])])]
                 else:
                     self.cores = ops.cp_als(data, ranks_cp, max_iter=max_iter, tol=tol)
-            elif ranks_tucker is not None or (eps is not None and not batch):
-                # tensor.py:401-408 / 436-439: exact TT first (the reference's _full_rank_tt), then round_tucker /
-                # round_tt / round on it.  The exact TT needs every Gram of the sweep to fit the direct eigensolver.
+            elif eps is not None and ranks_tucker is None and not batch:
+                # tensor.py:436-439: _full_rank_tt + round(eps) = round_tt(eps) then round_tucker with the left-over
+                # budget.  The exact TT is never formed: the dense sweep with the eps rank rule IS _full_rank_tt +
+                # round_tt(eps), and `reached` (tensor.py:2096, error of the rounded TT against the exact one) is the
+                # error against the dense data, measured by the device reconstruct-and-diff kernel.
+                self.cores = ops.ttsvd(data, rmax=None, eps=eps)
+                self.Us = [None] * N
+                reached = float(ops.tt_relative_error(data, self.cores))
+                if reached < eps:
+                    self.round_tucker((1 + eps) / (1 + reached) - 1, algorithm=algorithm)
+                Us = self.Us
+            elif ranks_tucker is not None:
+                # tensor.py:401-408: exact TT first (the reference's _full_rank_tt), then round_tucker / round_tt on it.
+                # The exact TT needs every Gram of the sweep to fit the direct eigensolver.
                 if batch:
                     raise NotImplementedError("batched Tucker rounding is not built")
+                if eps is not None:
+                    raise ValueError("Specify eps or ranks, but not both")
                 self.cores = ops.ttsvd(data, rmax=None, eps=0.0)
                 self.Us = [None] * N
-                if ranks_tucker is not None:
-                    self.round_tucker(rmax=ranks_tucker, algorithm=algorithm)
-                    if ranks_tt is not None:
-                        self.round_tt(rmax=ranks_tt, algorithm=algorithm)
-                else:
-                    self.round(eps, algorithm=algorithm)
+                self.round_tucker(rmax=ranks_tucker, algorithm=algorithm)
+                if ranks_tt is not None:
+                    self.round_tt(rmax=ranks_tt, algorithm=algorithm)
                 Us = self.Us
             elif batch:
                 # the reference's batch mode: per-sample decomposition, rank = min(rmax, len(S)), no eps
