@@ -102,5 +102,5 @@ def test_batch_mode_matches_per_sample():
 def test_unsupported_is_loud():
     from tntorch_b200 import ops
 
-    with pytest.raises(NotImplementedError):  # eps-only on a >256 Gram: raised, never faked
+    with pytest.raises(NotImplementedError):  # eps-only on a >256 Gram whose rank exceeds 240: raised, never faked
         ops.ttsvd(torch.randn(600, 600, device="cuda"), rmax=None, eps=1e-3)

@@ -144,7 +144,10 @@ inline int chfsi_rayleigh_ritz(const TB* G, int n, int b, TB** Xio, TB** Xtmp, C
   TNB_TRY((gemm_splitk<TB, TB, double, double, double>(pl, b, b, n, *Xio, b, false, w.W, b, false,
                                                        reinterpret_cast<double*>(w.partial), w.S, b, 1.0, nullptr, 0,
                                                        0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
-  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value, 2e-5));
+  // fp32 blocks: rotations in fp32 and a loose stop (the Ritz vectors are re-filtered anyway and stored in fp32);
+  // fp64 blocks: full accuracy, so that U = M V S^-1 built from the Ritz vectors is orthonormal to working precision
+  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value,
+                      std::is_same<TB, float>::value ? 2e-5 : 0.0));
   convert_kernel<double, TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.Tm, (int64_t)b * b);
   TNB_LAUNCH_CHECK();
   TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,
@@ -286,10 +289,9 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
     stats->converged = converged ? 1 : 0;
   }
   if (!use_chol) {
-    // a Cholesky breakdown was seen (numerically rank-deficient block, e.g. an exactly low-rank input): the
-    // eigen-decomposition based transform clamps the lost directions, which leaves the Ritz vectors orthonormal
-    // only to ~1e-5.  One Cholesky-QR pass in column order (= Gram-Schmidt: the leading, well-conditioned vectors
-    // are untouched by the clamped trailing pivots) restores them to working precision.
+    // a Cholesky breakdown was seen (numerically rank-deficient block): the eigen-decomposition based transform
+    // clamps the lost directions, which leaves the block orthonormal only approximately.  One Cholesky-QR pass in
+    // column order (= Gram-Schmidt: clamped trailing pivots do not touch the leading vectors) restores it.
     TNB_TRY(chfsi_orthonormalize<TB>(n, b, &X, &Xt, w, st, true));
   }
   TNB_CUDA(cudaMemcpyAsync(theta_out, w.lam, (size_t)b * sizeof(double), cudaMemcpyDeviceToDevice, st));
