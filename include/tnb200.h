@@ -70,6 +70,7 @@ int tnb_has_tensorcore_path(void);
  *   info_host  optional (may be NULL) 32 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix products,
  *              [3]=#tensor-core Gram launches; with TNB_FLAG_PROFILE also [4]=Gram ms, [5]=eigen ms,
  *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 7;
+ *              [29]=Jacobi sweeps summed over the Rayleigh-Ritz solves, [30]=#outer subspace iterations,
  *              [31]=#Chebyshev filters that ran as one resident cluster kernel
  * ------------------------------------------------------------------------------------------ */
 int64_t tnb_ttsvd_cores_capacity(int ndim, const int64_t* shape, const int32_t* rmax, int64_t* core_offsets_host);

@@ -18,6 +18,7 @@ namespace tnb {
 
 struct ChfsiStats {
   int fused_filters = 0;  // filters that ran as one resident kernel (cheb_filter.cuh)
+  int rr_sweeps = 0;      // Jacobi sweeps summed over the Rayleigh-Ritz solves (diagnostic)
   int products = 0;  // number of G*X block products
   int outer = 0;
   int converged = 0;
@@ -269,6 +270,7 @@ inline int eig_topk_chfsi(const TB* G, int n, int k, int b, const double* d_trac
     TNB_CUDA(cudaStreamSynchronize(st));
     double cap = 0.0;
     for (int i = 0; i < k; ++i) cap += h_theta[i];
+    if (stats) stats->rr_sweeps += h_flag[0] < 0 ? -h_flag[0] : h_flag[0];
     if (h_flag[1] != 0) {
       // Cholesky saw numerically dependent columns: this iteration's basis is unreliable; go back to the
       // eigen-decomposition based transform for the rest of the solve and do not test convergence now

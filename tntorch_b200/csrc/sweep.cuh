@@ -222,7 +222,9 @@ inline int eig_solve_and_rank(const double* G, const TBk* Gb, int64_t L, EigWork
   for (;;) {
     ChfsiStats cs;
     TNB_TRY(eig_run<TBk>(G, Gb, L, ew, &sc->trace, &cs, st, allow_tc, shared_gpu, k_try, tol));
-    if (total) total->products += cs.products, total->fused_filters += cs.fused_filters, total->outer += cs.outer;
+    if (total)
+      total->products += cs.products, total->fused_filters += cs.fused_filters, total->outer += cs.outer,
+          total->rr_sweeps += cs.rr_sweeps;
     if (solves) *solves += 1;
     rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.k_run : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, sc);
     TNB_LAUNCH_CHECK();
@@ -248,6 +250,7 @@ struct SweepInfo {
   int eig_solves = 0;
   int chfsi_products = 0;
   int fused_filters = 0;  // Chebyshev filters run as one resident kernel (cheb_filter.cuh)
+  int rr_sweeps = 0, rr_solves = 0;  // Jacobi sweeps / solves of the Rayleigh-Ritz steps (diagnostic)
   int tc_grams = 0;
   // TNB_FLAG_PROFILE: CUDA-event timings (ms) on the launching stream, per step (t = 0 is the first Gram)
   int nsteps = 0;
@@ -329,7 +332,8 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   int solves = 0;
   TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, cx.sc, cx.h_sc, rm, batch_mode, &cs, &solves, st,
                                   cx.allow_tc, concurrent));
-  if (cx.info) cx.info->eig_solves += solves, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters;
+  if (cx.info) cx.info->eig_solves += solves, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters,
+        cx.info->rr_sweeps += cs.rr_sweeps, cx.info->rr_solves += cs.outer;
   prof.mark(st);
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(cx.h_sc);
   if (first_step && cx.info) cx.info->norm = std::sqrt(hs->norm2 > 0 ? hs->norm2 : 0.0);

@@ -94,6 +94,8 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
     info_host[3] = info.tc_grams;
     info_host[7] = info.nsteps;
     info_host[31] = info.fused_filters;
+    info_host[29] = info.rr_sweeps;
+    info_host[30] = info.rr_solves;
     for (int t = 0; t < info.nsteps && t < 7; ++t) {
       info_host[4] += info.gram_ms[t];
       info_host[5] += info.eig_ms[t];

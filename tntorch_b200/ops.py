@@ -103,7 +103,7 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
         cores.append(cores_buf[offs[k]: offs[k] + r0 * shape[k] * r1].view(r0, shape[k], r1))
     if return_info:
         return cores, dict(norm=info[0], eig_solves=int(info[1]), chfsi_products=int(info[2]), tc_grams=int(info[3]),
-                           fused_filters=int(info[31]))
+                           fused_filters=int(info[31]), rr_sweeps=int(info[29]), outer_iterations=int(info[30]))
     return cores
 
 
