@@ -129,6 +129,8 @@ TTSVD_CASES = {
     # eps-only with a Gram matrix larger than the direct eigensolver (step 1: 320 / 288 columns): the leading values
     # come from the subspace iteration in growing blocks until the tail-energy rule is decided
     "eps_biggram_f32": dict(kind="tt_noise", shape=(40,) * 4, rank=8, noise=1e-3, seed=12, dtype="float32", eps=2e-2, big=True),
+    # a finer budget (delta^2 / ||T||^2 = 1.3e-6): below the resolution of the TF32 Gram, the sweep must take the exact one
+    "eps_fine_f32": dict(kind="tt_noise", shape=(40,) * 4, rank=8, noise=1e-4, seed=14, dtype="float32", eps=2e-3, big=True),
     "eps_biggram_f64": dict(kind="tt_noise", shape=(24,) * 4, rank=12, noise=1e-6, seed=13, dtype="float64", eps=1e-4),
     # tutorial known answers (docs/tutorials/decompositions.ipynb:68,361)
     "analytic128_r3": dict(kind="analytic128", dtype="float64", ranks_tt=3, big=False),

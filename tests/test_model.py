@@ -49,3 +49,22 @@ def test_chfsi_captures_optimal_energy(kind):
     deficit = (w[:r].sum() - np.trace(V.T @ G @ V)) / np.trace(G)
     assert deficit < 1e-7
     assert nprod < 400
+
+
+def test_tf32_gram_is_a_uniform_scaling():
+    """Why the tensor-core Gram (operands truncated to TF32 by the hardware) is safe for the rank rule, and where it
+    stops being so (csrc/sweep.cuh, `tc_gram`): truncation shrinks every product by nearly the same factor, so
+    G_tf32 = (1 - c) G + E with c ~ 7e-4 and ||E|| ~ 2e-6 ||G||: eigenvectors and eigenvalue RATIOS survive, absolute
+    tails below ~1e-6 of the trace do not."""
+    rng = np.random.default_rng(0)
+    K, n, r = 100000, 64, 6
+    A = (rng.standard_normal((K, r)) @ rng.standard_normal((r, n)) + 1e-3 * rng.standard_normal((K, n))).astype(np.float32)
+    At = (A.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+    A64 = A.astype(np.float64)
+    G, Gt = A64.T @ A64, At.T @ At
+    c = 1.0 - np.trace(Gt) / np.trace(G)
+    assert 3e-4 < c < 1.5e-3
+    assert np.linalg.norm(Gt - (1 - c) * G, 2) / np.linalg.norm(G, 2) < 5e-6
+    w, wt = np.linalg.eigvalsh(G)[::-1], np.linalg.eigvalsh(Gt)[::-1]
+    assert np.allclose(wt[:r] / w[:r], 1 - c, atol=5e-6)          # the signal spectrum is scaled, not distorted
+    assert abs(wt[r:].sum() / wt.sum() - w[r:].sum() / w.sum()) < 2e-6  # tail fractions are good to ~1e-6 only

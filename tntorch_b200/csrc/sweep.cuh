@@ -300,7 +300,12 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   cudaStream_t st = cx.st;
   GramWork<T> gw;
   EigWork<TBk> ew;
-  gram_carve<T>(ar, rows, n, cx.allow_tc, gw);
+  // The TF32 Gram equals (1 - c) * G, c ~ 7e-4 (operand truncation shrinks every product alike: harmless, the rank
+  // rule works on ratios) plus noise of ~1.6e-6 * ||G|| (measured, tests/test_model.py) — a floor under the tail
+  // energies the rank rule can resolve.  An eps budget between "inactive" and 1e-4 of the trace needs finer
+  // resolution than that: those sweeps take the exact-product fp64-accumulating Gram instead.
+  const bool tc_gram = cx.allow_tc && (dry || cx.eps_scaled2 < 1e-20 || cx.eps_scaled2 >= 1e-4);
+  gram_carve<T>(ar, rows, n, tc_gram, gw);
   double* G = ar.template take<double>((size_t)L * L);
   float* Gf = nullptr;
   const int64_t kcap = std::min<int64_t>(rank_cap, L);
@@ -322,7 +327,7 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   const bool concurrent = (cx.flags & TNB_FLAG_CONCURRENT) != 0;
   {
     BigKernelGate gate(st, concurrent && gw.tc_ws != nullptr);
-    TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, cx.allow_tc, &used_tc, st));
+    TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, tc_gram, &used_tc, st));
   }
   if (cx.info) cx.info->tc_grams += used_tc;
   trace_kernel<<<1, 256, 0, st>>>(G, (int)L, (int)L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
