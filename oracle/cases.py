@@ -182,11 +182,22 @@ CP_CASES = {
 CROSS_CASES = {
     "cfg5_32x6_r10": dict(N=6, I=32, lo=0.0, hi=1.0, shift=1.0, ranks_tt=10, max_iter=3, seed=60),
     "adaptive_32x5": dict(N=5, I=32, lo=1.0, hi=32.0, shift=0.0, kickrank=3, eps=1e-6, max_iter=25, seed=61),
-    "small_10x3_r3": dict(N=3, I=10, lo=1.0, hi=10.0, shift=0.0, ranks_tt=3, max_iter=5, seed=62),
+    "small_10x3_r3": dict(N=3, I=10, lo=1.0, hi=10.0, shift=0.0, ranks_tt=3, max_iter=5, seed=62, forward=True),
+    # _minimize mode (cross.py:342-359): sum_i (x_i - 0.37)^2 on a 16^4 grid, minimum 4 * 0.03^2 at index (6, 6, 6, 6)
+    "minimize_16x4": dict(N=4, I=16, lo=0.0, hi=1.0, ranks_tt=4, max_iter=4, seed=63, minimize=True, fn="bowl"),
 }
 
 
-def cross_function(shift):
+def cross_function(shift, fn=None):
+    if fn == "bowl":
+        def bowl(*xs):
+            s = xs[0] * 0
+            for x in xs:
+                s = s + (x - 0.37) ** 2
+            return s
+
+        return bowl
+
     def f(*xs):
         s = xs[0] * 0 + shift
         for x in xs:

@@ -155,12 +155,22 @@ def gen_cross():
         torch.manual_seed(spec["seed"])
         domain = [torch.linspace(spec["lo"], spec["hi"], spec["I"], dtype=torch.float64) for _ in range(spec["N"])]
         kw = {k: spec[k] for k in ("ranks_tt", "kickrank", "eps", "max_iter") if k in spec}
-        t, info = tn.cross(cases.cross_function(spec["shift"]), domain=domain, verbose=False, return_info=True,
-                           suppress_warnings=True, **kw)
+        fn = cases.cross_function(spec.get("shift", 0.0), spec.get("fn"))
+        if spec.get("minimize"):
+            kw["_minimize"] = True
+        t, info = tn.cross(fn, domain=domain, verbose=False, return_info=True, suppress_warnings=True, **kw)
+        if spec.get("minimize"):
+            out[f"{name}/min"] = np.float64(float(info["min"]))
+            out[f"{name}/argmin"] = np.asarray(info["argmin"], dtype=np.int64)
+            print(name, "min", float(info["min"]), "argmin", info["argmin"], flush=True)
+        if spec.get("forward"):
+            tf = tn.cross_forward(info, fn, domain=domain)
+            out[f"{name}/forward_full"] = tf.torch().double().numpy()
+            out[f"{name}/cross_full"] = t.torch().double().numpy()
         full_err = None
-        if spec["I"] ** spec["N"] <= 40_000_000:
+        if spec["I"] ** spec["N"] <= 40_000_000 and not spec.get("minimize"):
             grids = torch.meshgrid(*domain, indexing="ij")
-            gt = cases.cross_function(spec["shift"])(*grids)
+            gt = fn(*grids)
             full_err = float(torch.norm(gt - t.torch()) / torch.norm(gt))
             out[f"{name}/full_relerr"] = np.float64(full_err)
         out[f"{name}/val_eps"] = np.float64(float(info["val_eps"]))

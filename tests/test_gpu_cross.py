@@ -73,19 +73,46 @@ def test_cross_matches_reference(name):
     torch.manual_seed(spec["seed"])
     domain = [torch.linspace(spec["lo"], spec["hi"], spec["I"], dtype=torch.float64) for _ in range(spec["N"])]
     kw = {k: spec[k] for k in ("ranks_tt", "kickrank", "eps", "max_iter") if k in spec}
-    t, info = tnb.cross(cases.cross_function(spec["shift"]), domain=domain, verbose=False, return_info=True,
-                        suppress_warnings=True, **kw)
+    fn = cases.cross_function(spec.get("shift", 0.0), spec.get("fn"))
+    if spec.get("minimize"):
+        kw["_minimize"] = True
+    t, info = tnb.cross(fn, domain=domain, verbose=False, return_info=True, suppress_warnings=True, **kw)
     assert list(info["Rs"]) == list(g[f"{name}/Rs"])
     assert int(info["nsamples"]) == int(g[f"{name}/nsamples"])
+    if spec.get("minimize"):  # cross.py:342-359: running minimum and its multi-index
+        assert abs(float(info["min"]) - float(g[f"{name}/min"])) <= 1e-12
+        assert tuple(int(v) for v in info["argmin"]) == tuple(int(v) for v in g[f"{name}/argmin"])
+        return
     ref = float(g[f"{name}/val_eps"])
     got = float(info["val_eps"])
     assert got <= max(10 * ref, 1e-9) and (ref < 1e-6 or abs(got - ref) <= 0.5 * ref)
     if f"{name}/full_relerr" in g.files:
         grids = torch.meshgrid(*[d.cuda() for d in domain], indexing="ij")
-        gt = cases.cross_function(spec["shift"])(*grids)
+        gt = fn(*grids)
         err = float(torch.norm(gt - t.torch()) / torch.norm(gt))
         fref = float(g[f"{name}/full_relerr"])
         assert err <= max(10 * fref, 1e-9)
+    if spec.get("forward"):  # cross.py:532-644: the replay reproduces the cross result, and the reference's replay
+        tf = tnb.cross_forward(info, fn, domain=domain)
+        full = t.torch()
+        assert float(torch.norm(tf.torch() - full) / torch.norm(full)) < 1e-9
+        ref_fwd = torch.as_tensor(g[f"{name}/forward_full"]).cuda()
+        assert float(torch.norm(tf.torch() - ref_fwd) / torch.norm(ref_fwd)) < 1e-6
+
+
+def test_cross_forward_is_differentiable():
+    """cross_forward exists so that the TT depends differentiably on parameters of the black-box function."""
+    import tntorch_b200 as tnb
+
+    np.random.seed(3); torch.manual_seed(3)
+    dom = [torch.linspace(1, 2, 12, dtype=torch.float64) for _ in range(3)]
+    a = torch.tensor(1.5, dtype=torch.float64, device="cuda", requires_grad=True)
+    t, info = tnb.cross(lambda x, y, z: 1.0 / (x + y + 1.5 * z), domain=dom, ranks_tt=3, verbose=False, return_info=True,
+                        suppress_warnings=True)
+    tf = tnb.cross_forward(info, lambda x, y, z: 1.0 / (x + y + a * z), domain=dom)
+    loss = sum((c ** 2).sum() for c in tf.cores)
+    loss.backward()
+    assert a.grad is not None and torch.isfinite(a.grad) and float(a.grad.abs()) > 0
 
 
 def test_cross_reference_test_suite_cases():

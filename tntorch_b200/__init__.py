@@ -5,7 +5,7 @@ Drop-in surface for that path: ``Tensor(data, ranks_tt=/eps=)``, ``Tensor.round_
 """
 from .round import relative_error, round, round_tt, round_tucker, truncated_svd  # noqa: F401
 from .tensor import Tensor  # noqa: F401
-from .cross import cross, meshgrid  # noqa: F401
+from .cross import cross, cross_forward, meshgrid  # noqa: F401
 from . import ops  # noqa: F401
 
 __version__ = "0.1.0"

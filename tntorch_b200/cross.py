@@ -81,8 +81,11 @@ def cross(
     detach_evaluations=False,
 ):
     """Cross-approximation of `function` over a tensor-product domain (see tntorch.cross)."""
-    if _minimize:
-        raise NotImplementedError("rect_maxvol / _minimize mode is a next row of SURVEY.md §8f and not built yet")
+    # _minimize (cross.py:342-359, 399-400): the samples are mapped through pi/2 - atan(f - min) before the maxvol
+    # step, the running minimum and its multi-index are tracked, and the index search is the reference's
+    # rect_maxvol(Q, maxK=r) — which with maxK = r never adds a row and is exactly maxvol stopped after
+    # start_maxvol_iters = 10 swaps (maxvol.py:52-84).
+    mv_iters = 10 if _minimize else 100
     assert domain is not None or tensors is not None
     assert function_arg in ("vectors", "matrix")
     if device is None:
@@ -168,6 +171,16 @@ def cross(
             info["sample_positions"] = torch.cat((info["sample_positions"], torch.stack(Xs, dim=1)), dim=0)
             info["sample_values"] = torch.cat((info["sample_values"], evaluation))
         info["eval_time"] += time.time() - t0
+        if _minimize:
+            shifted = np.pi / 2 - torch.atan(evaluation - info["min"])
+            am = torch.argmax(shifted)
+            eval_min = torch.tan(np.pi / 2 - shifted[am]) + info["min"]
+            if (isinstance(info["min"], (int, float)) and info["min"] == 0) or bool(eval_min < info["min"]):
+                c0, c1, c2 = np.unravel_index(int(am), [int(Rs[j]), Is[j], int(Rs[j + 1])])
+                info["min"] = eval_min
+                info["argmin"] = (tuple(int(v) for v in lsets[j][c0][1:].tolist()) + (int(c1),)
+                                  + tuple(int(v) for v in rsets[j][c2][:-1].tolist()))
+            evaluation = shifted
         if evaluation.dim() == 2:
             evaluation = evaluation[:, 0]
         bad = torch.isnan(evaluation) | torch.isinf(evaluation)
@@ -189,7 +202,7 @@ def cross(
         for j in range(N - 1):
             V = evaluate_function(j).reshape(-1, int(Rs[j + 1]))
             Q = ops.qr(V)  # Householder QR on the device
-            local, C = ops.maxvol(Q)  # local: int32 [R_{j+1}], C = Q inv(Q[local])  (= the lstsq of cross.py:403)
+            local, C = ops.maxvol(Q, max_iters=mv_iters)  # local: int32 [R_{j+1}], C = Q inv(Q[local])  (= the lstsq of cross.py:403)
             cores[j] = C.to(V.dtype).reshape(int(Rs[j]), Is[j], int(Rs[j + 1]))
             local = local.long()
             left_locals.append(local)
@@ -202,7 +215,7 @@ def cross(
         for j in range(N - 1, 0, -1):
             V = evaluate_function(j).reshape(int(Rs[j]), -1)
             Q = ops.qr(V.t().contiguous())
-            local, C = ops.maxvol(Q)
+            local, C = ops.maxvol(Q, max_iters=mv_iters)
             cores[j] = C.t().to(V.dtype).reshape(int(Rs[j]), Is[j], int(Rs[j + 1]))
             local = local.long()
             local_i = torch.div(local, int(Rs[j + 1]), rounding_mode="floor")
@@ -255,3 +268,60 @@ def cross(
         info["val_eps"] = val_eps
         return ret, info
     return ret
+
+
+def cross_forward(info, function=lambda x: x, domain=None, tensors=None, function_arg="vectors", return_info=False):
+    """cross.py:532-644: replay of a finished cross run.  Given the index sets `tn.cross(..., return_info=True)`
+    recorded (`lsets`, `rsets`, `left_locals`, `Rs`), evaluate the function on those fibres again and assemble the TT
+    by the cross-interpolation formula (core_j = V (V[left_local_j])^-1, last core = the fibres themselves) with torch
+    operations only, so the result is differentiable w.r.t. whatever `function` closes over."""
+    assert domain is not None or tensors is not None
+    assert function_arg in ("vectors", "matrix")
+    if function_arg == "matrix":
+        def f(*args):
+            return function(torch.cat([arg[:, None] for arg in args], dim=1))
+    else:
+        f = function
+    device = None
+    if tensors is None:
+        device = domain[0].device
+        if device.type != "cuda":
+            device = torch.device("cuda")
+        tensors = meshgrid(domain, device=device)
+    if not hasattr(tensors, "__len__"):
+        tensors = [tensors]
+    if device is None:
+        device = tensors[0].cores[0].device
+    Is = list(tensors[0].shape)
+    N = len(Is)
+    lsets = [torch.as_tensor(np.asarray(l), dtype=torch.long, device=device) for l in info["lsets"]]
+    rsets = [torch.as_tensor(np.asarray(r), dtype=torch.long, device=device) for r in info["rsets"]]
+    left_locals = [torch.as_tensor(np.asarray(l), dtype=torch.long, device=device) for l in info["left_locals"]]
+    Rs = [int(r) for r in info["Rs"]]
+    if return_info:
+        info["Xs"] = torch.zeros(0, N)
+        info["shapes"] = []
+    t_lin, t_rin = _init_interfaces(tensors, rsets, N, device)
+
+    def evaluate_function(j):
+        Xs = [torch.einsum("ai,ibj,jc->abc", t_lin[k][j], t.cores[j], t_rin[k][j]).flatten() for k, t in enumerate(tensors)]
+        evaluation = f(*Xs)
+        if return_info:
+            info["Xs"] = torch.cat((info["Xs"], torch.stack(Xs, dim=1).detach().cpu()), dim=0)
+            info["shapes"].append([Rs[j], Is[j], Rs[j + 1]])
+        return evaluation.reshape(Rs[j], Is[j], Rs[j + 1])
+
+    cores = []
+    for j in range(N - 1):
+        V = evaluate_function(j).reshape(-1, Rs[j + 1])
+        A = V[left_locals[j], :]
+        X = torch.linalg.solve(A.t(), V.t()).t()  # lstsq of a square, well-conditioned (maxvol) system: cross.py:620
+        cores.append(X.reshape(Rs[j], Is[j], Rs[j + 1]))
+        local_r = torch.div(left_locals[j], Is[j], rounding_mode="floor")
+        local_i = left_locals[j] - local_r * Is[j]
+        lsets[j + 1] = torch.cat([lsets[j][local_r, :], local_i[:, None]], dim=1)
+        for k, t in enumerate(tensors):
+            t_lin[k][j + 1] = torch.einsum("ai,iaj->aj", t_lin[k][j][local_r, :], t.cores[j][:, local_i, :])
+    cores.append(evaluate_function(N - 1))
+    out = Tensor(cores)
+    return (out, info) if return_info else out
