@@ -46,6 +46,7 @@ def parse():
 
 
 METRIC = "TT-SVD GElements/s"
+_json_out = sys.stdout  # replaced in __main__ by a duplicate of the real fd 1 (everything else goes to stderr)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,7 +120,7 @@ def run_reference(args):
                                    f"thread count picked among 8/16/32/64/all"},
         "e2e": {"value": value, "unit": "GElements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_json_out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -475,13 +476,18 @@ def run_ours(args):
             "e2e": e2e,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner at communicator
+    # creation, torchrun notices) is routed to stderr by pointing fd 1 at fd 2 for the whole run
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     if a.impl == "reference":
         run_reference(a)
     else:
