@@ -313,6 +313,7 @@ def run_ours(args):
     phase = {"gram_ms": [], "eig_ms": [], "factor_ms": []}
     nprof = 3
     acc = np.zeros(32)
+    prof_plan.run(X)  # untimed: the single-stream schedule uses kernels (resident filter) the concurrent steps did not load yet
     for _ in range(nprof):
         prof_plan.run(X)
         acc += np.array(list(prof_plan.info))
