@@ -55,3 +55,33 @@ def test_shard_range_partitions():
             assert ranges[0][0] == 0 and ranges[-1][1] == batch
             assert all(ranges[g][1] == ranges[g + 1][0] for g in range(world - 1))
             assert max(h - l for l, h in ranges) - min(h - l for l, h in ranges) <= 1
+
+
+def _worker_generic(rank, world, port, batch):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tntorch_b200.dist import batch_sharded, shard_range
+
+    solved = []
+
+    def solve(p):  # stands in for ops.tt_round / ops.cp_als / cross(...).cores: ragged list of tensors per problem
+        solved.append(p)
+        return [torch.full((p % 3 + 1, 2), float(p)), torch.full((3, p % 2 + 1), float(-p))]
+
+    out = batch_sharded(list(range(batch)), solve)
+    lo, hi = shard_range(batch, world, rank)
+    assert solved == list(range(lo, hi))  # every rank solved only its own slice, in order
+    assert len(out) == batch
+    for p, fac in enumerate(out):
+        assert fac[0].shape == (p % 3 + 1, 2) and fac[1].shape == (3, p % 2 + 1)
+        assert float(fac[0][0, 0]) == float(p) and float(fac[1][0, 0]) == float(-p)
+    local_only = batch_sharded(list(range(batch)), solve, gather=False)
+    assert len(local_only) == hi - lo
+    dist.destroy_process_group()
+
+
+def test_batch_sharded_driver_world2():
+    """The driver behind round_tt_/cp_als_/cross_batch_sharded (BASELINE configs 3-5 shard over the batch)."""
+    port = _free_port()
+    mp.spawn(_worker_generic, args=(2, port, 7), nprocs=2, join=True)

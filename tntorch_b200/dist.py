@@ -63,3 +63,38 @@ def ttsvd_batch_sharded(tensors: Sequence[torch.Tensor], rmax=None, eps: float =
     lo, hi = shard_range(len(tensors), world, rank)
     local = [ops.ttsvd(tensors[i], rmax=rmax, eps=eps) for i in range(lo, hi)]
     return all_gather_cores(local, len(tensors)) if gather else local
+
+
+def batch_sharded(problems: Sequence, solve, gather: bool = True):
+    """The sharding pattern shared by every batched workload of the path (BASELINE.json configs 3-5): rank g solves
+    the contiguous slice of `problems` it owns with `solve(problem) -> list of tensors` (TT cores or CP factors), no
+    collective in between, then ONE all-gather of the ragged results."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(len(problems), world, rank)
+    local = [list(solve(problems[i])) for i in range(lo, hi)]
+    return all_gather_cores(local, len(problems)) if gather else local
+
+
+def round_tt_batch_sharded(tts: Sequence[Sequence[torch.Tensor]], rmax=None, eps: float = 1e-14, gather: bool = True):
+    """config 3 in batch form: a list of TT tensors (lists of cores), each rounded on the rank that owns it."""
+    from . import ops
+
+    return batch_sharded(tts, lambda cores: ops.tt_round(list(cores), eps=eps, rmax=rmax), gather)
+
+
+def cp_als_batch_sharded(tensors: Sequence[torch.Tensor], R: int, max_iter: int = 25, tol: float = 1e-4, gather: bool = True):
+    """config 4 ("1 vs 8 B200 batch-sharded"): independent CP-ALS problems, one per owned tensor."""
+    from . import ops
+
+    return batch_sharded(tensors, lambda X: ops.cp_als(X, R, max_iter=max_iter, tol=tol), gather)
+
+
+def cross_batch_sharded(functions: Sequence, domain, gather: bool = True, **cross_kw):
+    """config 5 (B black-box functions on the same grid, sharded over the GPUs): `tn.cross` per owned function.
+    The reference has no batch support in `cross` (cross.py:256-258); the batch is a loop here too, per rank."""
+    from .cross import cross
+
+    kw = dict(verbose=False, suppress_warnings=True)
+    kw.update(cross_kw)
+    return batch_sharded(functions, lambda f: cross(f, domain=domain, **kw).cores, gather)
