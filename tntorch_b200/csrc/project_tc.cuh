@@ -17,8 +17,10 @@
 // What bounds it (measured, profiles/r01_ncu_summaries.md): a tcgen05.mma of M=128, K=8 occupies the tensor pipe for
 // ~100 (TS) to ~140 (SS) cycles however small N is, and one thread issues all of them, so the MMA-issuing thread
 // paces the CTA: 8 instructions per 16 KB chunk.  With all-TS operands and no integer divisions in that thread's
-// loop the chunk time drops below the HBM feed for K = 64 (5.76 TB/s = 88 % of the measured copy peak); for
-// K = 2048 the 8 KB row pitch leaves 256-byte DRAM bursts per page and the kernel stays at ~4.4 TB/s.
+// loop a chunk takes ~1050 cycles: A is ingested at ~4.4 TB/s whatever K is (K = 64 .. 2048, V resident or streamed,
+// scripts/gpu_proj_k.py); with the output of the K = 64 step (half the input again) that is 5.8 TB/s = 88 % of the
+// measured copy peak.  Halving the instruction count needs the operands swapped (V stack on the M side, 256 rows of A
+// per instruction on the N side).
 #pragma once
 #include "gram_tc.cuh"
 
