@@ -107,6 +107,10 @@ int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t
  *   delta < 0 means "not given"; eps < 0 means "not given"; both given -> TNB_ERR_INVALID
  *   (round.py:77-78 ValueError).  rmax <= 0 means no cap.  left/right need m*min(m,n) and
  *   min(m,n)*n elements of capacity; *rank_host receives r.
+ *   left_ortho: bit 0 = which factor is orthonormal (round.py:164-183); bit 1 = the reference's batch rank rule
+ *   for one sample of a batch (round.py:149-150: r = min(rmax, len(S)), eps/delta ignored).  In that mode a zero
+ *   sample keeps that rank (zero factors) and *rank_host receives -r, so the caller can apply round.py:138-142
+ *   (rank-1 zeros only when every sample is zero).
  * ------------------------------------------------------------------------------------------ */
 size_t tnb_truncated_svd_workspace_bytes(int dtype, int64_t m, int64_t n);
 int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double delta, double eps, int32_t rmax,

@@ -216,3 +216,56 @@ TUCKER_CASES = {
     "tt_round_tucker_rmax": dict(kind="tt", spec=dict(shape=(12, 14, 10, 9), rank=5, seed=72, dtype="float64"), round_tucker=dict(rmax=4)),
     "tt_round_eps": dict(kind="tt", spec=dict(shape=(10,) * 5, rank=7, seed=24, dtype="float64"), round=dict(eps=0.3)),
 }
+
+
+# ---- full-size cases of BASELINE.json configs 2-4 (golden outputs: oracle/gen_golden_full.py -> tests/golden/full.npz) -----
+def make_dense_big(spec):
+    """Full-size inputs, built in fp32 with bounded host memory (one 4 GiB array + one temporary)."""
+    shape, seed = spec["shape"], spec["seed"]
+    n = int(np.prod(shape))
+    if spec["kind"] == "randn":
+        return _rng(seed).standard_normal(n, dtype=np.float32).reshape(shape)
+    if spec["kind"] == "tt_noise":
+        cores = random_tt(shape, spec["rank"], seed, np.float64)
+        h = len(shape) // 2
+        left = tt_full_matrix(cores[:h]).astype(np.float32)          # (prod I_<h) x r
+        right = tt_full_matrix(cores[h:], left_open=True).astype(np.float32)  # r x (prod I_>=h)
+        X = left @ right
+        std = float(np.sqrt(np.mean(np.square(X[:: max(1, X.shape[0] // 64)], dtype=np.float64))))
+        noise = _rng(seed + 1).standard_normal(n, dtype=np.float32).reshape(X.shape)
+        noise *= np.float32(spec["noise"] * std)
+        X += noise
+        return X.reshape(shape)
+    raise ValueError(spec["kind"])
+
+
+def tt_full_matrix(cores, left_open=False):
+    """Contract a chain of TT cores into a matrix: (prod I) x r_last, or r_first x (prod I) when left_open."""
+    if left_open:
+        f = np.eye(cores[0].shape[0])
+        for c in cores:
+            f = (f.reshape(-1, c.shape[0]) @ c.reshape(c.shape[0], -1)).reshape(cores[0].shape[0], -1, c.shape[2])
+            f = f.reshape(cores[0].shape[0], -1)
+            f = f.reshape(cores[0].shape[0], -1, c.shape[2]).reshape(-1, c.shape[2]) if c is not cores[-1] else f
+        return f.reshape(cores[0].shape[0], -1)
+    f = np.ones((1, cores[0].shape[0]))
+    for c in cores:
+        f = (f @ c.reshape(c.shape[0], -1)).reshape(-1, c.shape[2])
+    return f
+
+
+FULL_TTSVD_CASES = {
+    # BASELINE configs[1] stand-ins (SURVEY §8d): the bench tensor's character, and the structured twin
+    "twin64x5_r32_f32": dict(kind="tt_noise", shape=(64,) * 5, rank=32, noise=1e-2, seed=109, dtype="float32", ranks_tt=32),
+    "randn64x5_r32_f32": dict(kind="randn", shape=(64,) * 5, seed=108, dtype="float32", ranks_tt=32),
+}
+FULL_ROUND_CASES = {
+    # BASELINE configs[2] exactly as named: tn.randn([128]*10, ranks_tt=64) -> round_tt(rmax=16), fp64
+    "cfg3_128x10_r64to16_f64": dict(shape=(128,) * 10, rank=64, seed=123, dtype="float64", rmax=16),
+    # reference tests/test_round.py:52-59 at that size: t + t -> round_tt(eps=1e-8) returns rank 64
+    "cfg3_doubled_128x10_r32_f64": dict(shape=(128,) * 10, rank=32, seed=124, dtype="float64", doubled=True, eps=1e-8),
+}
+FULL_CP_CASES = {
+    # BASELINE configs[3] at the CPU-feasible size of BASELINE.md §4: R=50 on 64^4, fp64 oracle, 10 sweeps
+    "cp_64x4_R50": dict(shape=(64,) * 4, Rtrue=50, R=50, sweeps=10, noise=1e-2, seed=150, dtype="float64"),
+}

@@ -30,9 +30,10 @@ def _worker(rank, world, port, batch):
     local = []
     for i in range(lo, hi):
         r = 2 + i % 3
-        local.append([torch.full((1, 4, r), float(i)), torch.full((r, 5, 1), float(i) + 0.5)])
-    allc = all_gather_cores(local, batch)
+        local.append([torch.full((1, 4, r), float(i), dtype=torch.float64), torch.full((r, 5, 1), float(i) + 0.5, dtype=torch.float64)])
+    allc = all_gather_cores(local, batch)  # batch < world: a rank with no problem takes dtype from the metadata
     assert len(allc) == batch
+    assert all(c.dtype == torch.float64 for cores in allc for c in cores)
     for i, cores in enumerate(allc):
         r = 2 + i % 3
         assert cores[0].shape == (1, 4, r) and cores[1].shape == (r, 5, 1)
@@ -40,7 +41,7 @@ def _worker(rank, world, port, batch):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch", [5, 2])
+@pytest.mark.parametrize("batch", [5, 2, 1])
 def test_all_gather_ragged_cores_world2(batch):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, batch), nprocs=2, join=True)

@@ -259,8 +259,16 @@ inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], i
     last_error_ref() = "resident filter: shape outside the envelope or workspace too small";
     return TNB_ERR_UNSUPPORTED;
   }
-  static unsigned refused = 0;  // sizes whose cooperative launch the driver refused once
-  if (refused & (1u << (n / 256))) return TNB_ERR_UNSUPPORTED;
+  // everything remembered about the launch is per device: refused sizes, the chaining event, the cluster occupancy
+  struct DevState {
+    std::mutex mu;
+    cudaEvent_t last = nullptr;
+    int max_clusters = -1;  // co-resident clusters of 8 CTAs at the largest footprint
+    unsigned refused = 0;   // sizes whose cooperative launch the driver refused once
+  };
+  static DevState states[TNB_MAX_DEVICES];
+  DevState& ds = states[current_device_index()];
+  if (ds.refused & (1u << (n / 256))) return TNB_ERR_UNSUPPORTED;
   ChebFilterParams p;
   p.n = n;
   p.b = b;
@@ -278,10 +286,9 @@ inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], i
   TNB_TRY(encode_rowmajor_f32(&tg, G, n, n));
   for (int i = 0; i < 3; ++i) TNB_TRY(encode_rowmajor_f32(&ty[i], bufs[i], n, b));
   const size_t smem = cheb_filter_smem_bytes(n, b);
-  static std::mutex mu;
-  static cudaEvent_t last = nullptr;
-  static int max_clusters = -1;  // co-resident clusters of 8 CTAs at the largest footprint
-  std::lock_guard<std::mutex> lk(mu);
+  std::lock_guard<std::mutex> lk(ds.mu);
+  cudaEvent_t& last = ds.last;
+  int& max_clusters = ds.max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((n / 128) * CF_KS));
   cfg.blockDim = dim3(CF_THREADS);
@@ -318,7 +325,7 @@ inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], i
     fail(TNB_ERR_UNSUPPORTED, "resident filter launch refused: %s (n=%d b=%d smem=%zu dsmem=%d, max active clusters %d)",
          cudaGetErrorString(e), n, b, smem, p.dsmem, max_clusters);
     if (getenv("TNB_DEBUG")) fprintf(stderr, "tnb200: %s\n", last_error_ref().c_str());
-    refused |= 1u << (n / 256);
+    ds.refused |= 1u << (n / 256);
     return TNB_ERR_UNSUPPORTED;
   }
   TNB_CUDA(cudaEventRecord(last, st));

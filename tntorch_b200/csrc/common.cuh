@@ -119,6 +119,28 @@ inline const DeviceInfo& device_info() {
   return info;
 }
 
+// Per-device caches: cudaFuncSetAttribute, events and occupancy answers belong to ONE device, so everything that
+// remembers "already done" is indexed by the current device ordinal (a process may drive several GPUs, and several
+// host threads may share one).
+constexpr int TNB_MAX_DEVICES = 64;
+inline int current_device_index() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d % TNB_MAX_DEVICES;
+}
+struct PerDeviceFlag {
+  std::atomic<int> v[TNB_MAX_DEVICES];  // zero-initialised as a static
+};
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device); racing threads at worst set it twice.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(PerDeviceFlag& f, K kernel, int bytes) {
+  const int d = current_device_index();
+  if (f.v[d].load(std::memory_order_acquire)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) f.v[d].store(1, std::memory_order_release);
+  return e;
+}
+
 // SMs left free by the persistent / one-CTA-per-SM kernels (tensor-core Gram, projection).  With several
 // decompositions in flight on different streams the latency-bound one-CTA kernels of one tensor (Jacobi, Cholesky,
 // rank rule) then run beside the bandwidth-bound kernels of another instead of queueing behind them.
@@ -140,25 +162,32 @@ inline int usable_sms() {
 // products), which would otherwise queue behind — or steal an SM from and double the time of — a one-wave kernel.
 class BigKernelGate {
  public:
-  BigKernelGate(cudaStream_t st, bool enabled) : st_(st), on_(enabled) {
+  BigKernelGate(cudaStream_t st, bool enabled) : st_(st), on_(enabled), dev_(enabled ? current_device_index() : 0) {
     if (!on_) return;
     mu().lock();
-    if (!ev()) cudaEventCreateWithFlags(&ev(), cudaEventDisableTiming);
-    cudaStreamWaitEvent(st_, ev(), 0);
+    cudaEvent_t& e = ev();
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      e = nullptr;
+      cudaGetLastError();
+      return;  // no chaining possible: the kernels still run, only unordered against the other streams
+    }
+    if (cudaStreamWaitEvent(st_, e, 0) != cudaSuccess) cudaGetLastError();
   }
   ~BigKernelGate() {
     if (!on_) return;
-    cudaEventRecord(ev(), st_);
+    if (ev() && cudaEventRecord(ev(), st_) != cudaSuccess) cudaGetLastError();
     mu().unlock();
   }
   BigKernelGate(const BigKernelGate&) = delete;
   BigKernelGate& operator=(const BigKernelGate&) = delete;
 
  private:
-  static std::mutex& mu() { static std::mutex m; return m; }
-  static cudaEvent_t& ev() { static cudaEvent_t e = nullptr; return e; }
+  // one gate (mutex + event) per device: big kernels of different GPUs never wait on each other
+  std::mutex& mu() { static std::mutex m[TNB_MAX_DEVICES]; return m[dev_]; }
+  cudaEvent_t& ev() { static cudaEvent_t e[TNB_MAX_DEVICES] = {}; return e[dev_]; }
   cudaStream_t st_;
   bool on_;
+  int dev_;
 };
 
 // Pinned host scratch for reading small results back (ranks, Ritz values).

@@ -107,11 +107,8 @@ inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>
                                                          0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
     const size_t smem = (size_t)2 * b * (b | 1) * sizeof(double);
     const bool fits = smem <= (size_t)180 * 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-      TNB_CUDA(cudaFuncSetAttribute(chol_orth_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-      attr_set = true;
-    }
+    static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, chol_orth_kernel<TB>, 180 * 1024));
     chol_orth_kernel<TB><<<1, 1024, fits ? smem : 0, st>>>(w.S, b, w.jscratch, w.Tm, w.jinfo + 1, fits ? 1 : 0);
     TNB_LAUNCH_CHECK();
     TNB_TRY((gemm_direct<TB, TB, TB, TB>(n, b, b, *Xio, b, true, w.Tm, b, false, *Xtmp, b, (TB)1, nullptr, 0, (TB)0,

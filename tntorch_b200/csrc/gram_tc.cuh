@@ -490,11 +490,8 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(TNB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, gram_tc_kernel, TC_SMEM_BYTES));
   dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
   gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, tmap, p);
   TNB_LAUNCH_CHECK();
@@ -573,11 +570,8 @@ inline int atb_tc_f32(const float* A, int64_t K, int64_t m, const float* B, int6
   CUtensorMap ta, tb;
   TNB_TRY(encode_rowmajor_f32(&ta, A, K, m));
   TNB_TRY(encode_rowmajor_f32(&tb, B, K, n));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, gram_tc_kernel, TC_SMEM_BYTES));
   dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
   gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
   TNB_LAUNCH_CHECK();

@@ -234,11 +234,8 @@ inline int gram_tc2_f32(const float* A, int64_t rows, int64_t n, double* G, floa
   p.partial = static_cast<float*>(ws);
   CUtensorMap tmap;
   TNB_TRY(encode_rowmajor_f32(&tmap, A, rows, n));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, gram_tc2_kernel, TC2_SMEM_BYTES));
   dim3 grid((unsigned)(2 * p.num_tiles), (unsigned)p.ksplit);
   gram_tc2_kernel<<<grid, TC_THREADS, TC2_SMEM_BYTES, st>>>(tmap, p);
   TNB_LAUNCH_CHECK();

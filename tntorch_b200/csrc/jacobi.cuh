@@ -280,17 +280,14 @@ inline int jacobi_eigh(const double* G, int n, int ldg, double* w, double* V, do
   if (n < 1 || n > JACOBI_MAX_N) return fail(TNB_ERR_UNSUPPORTED, "jacobi_eigh: n=%d outside [1,%d]", n, JACOBI_MAX_N);
   const int np = n + (n & 1);
   const int max_sweeps = 30;
-  static bool attr_set = false;
   const int maxb = 2 * (JACOBI_SMEM_MAX_N) * (JACOBI_SMEM_MAX_N + 8) * (int)sizeof(double);
-  if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<double, true, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    TNB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel<float, true, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-    attr_set = true;
-  }
+  static PerDeviceFlag attr_done[6];
+  TNB_CUDA(ensure_dyn_smem(attr_done[0], jacobi_eigh_kernel<double, true, 8, 8>, maxb));
+  TNB_CUDA(ensure_dyn_smem(attr_done[1], jacobi_eigh_kernel<float, true, 8, 8>, maxb));
+  TNB_CUDA(ensure_dyn_smem(attr_done[2], jacobi_eigh_kernel<double, true, 8, 16>, maxb));
+  TNB_CUDA(ensure_dyn_smem(attr_done[3], jacobi_eigh_kernel<float, true, 8, 16>, maxb));
+  TNB_CUDA(ensure_dyn_smem(attr_done[4], jacobi_eigh_kernel<double, true, 16, 16>, maxb));
+  TNB_CUDA(ensure_dyn_smem(attr_done[5], jacobi_eigh_kernel<float, true, 16, 16>, maxb));
   if (single_precision) {
     const float tol = loose_tol > 0.0 ? (float)loose_tol : 2e-6f;  // default ~ eps_fp32 * sqrt(n)
     const size_t one = (size_t)np * (np + 8) * sizeof(float);

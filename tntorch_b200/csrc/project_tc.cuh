@@ -388,11 +388,8 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   TNB_TRY(encode_kmajor_f32(&ta, A, rows, K, PT_BM));
   TNB_TRY(encode_kmajor_f32(&th, Vhi, p.npad, K, p.npad));
   TNB_TRY(encode_kmajor_f32(&tl, Vlo, p.npad, K, p.npad));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNB_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, project_tc_kernel, PT_SMEM_BYTES));
   const int sms = usable_sms();
   const int64_t grid = p.num_row_blocks < sms ? p.num_row_blocks : sms;
   project_tc_kernel<<<(unsigned)grid, PT_THREADS, PT_SMEM_BYTES, st>>>(ta, th, tl, p);

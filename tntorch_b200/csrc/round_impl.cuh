@@ -128,11 +128,8 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
         TNB_CUDA(cudaMemsetAsync(jinfo, 0, 4 * sizeof(int), st));
         const size_t csm = (size_t)2 * cols * (cols | 1) * sizeof(double);
         const bool fits = csm <= (size_t)180 * 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-          TNB_CUDA(cudaFuncSetAttribute(chol_orth_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-          attr_set = true;
-        }
+        static PerDeviceFlag attr_done;
+  TNB_CUDA(ensure_dyn_smem(attr_done, chol_orth_kernel<T>, 180 * 1024));
         chol_orth_kernel<T><<<1, 1024, fits ? csm : 0, st>>>(G, (int)cols, js, fac, jinfo + 1, fits ? 1 : 0, Rf);
         TNB_LAUNCH_CHECK();
         TNB_CUDA(cudaMemcpyAsync(cx.h_sc, jinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -215,8 +212,11 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
 // ---------------------------------------------------------------------------------------------
 template <typename T, class ArenaT>
 inline int truncated_svd_impl(ArenaT& ar, bool dry, const T* M, int64_t m, int64_t n, double delta, double eps,
-                              int32_t rmax, int left_ortho, T* left, T* right, int32_t* rank_host, cudaStream_t st) {
+                              int32_t rmax, int left_ortho_flags, T* left, T* right, int32_t* rank_host,
+                              cudaStream_t st) {
   typedef T TBk;
+  const int left_ortho = left_ortho_flags & 1;
+  const int batch_mode = (left_ortho_flags & 2) ? 1 : 0;  // round.py:149-150: rank = min(rmax, len(S)), no eps, no zero branch
   const bool use_left = m <= n;  // round.py:102-107
   const int64_t L = use_left ? m : n;
   const int64_t K = use_left ? n : m;
@@ -229,7 +229,10 @@ inline int truncated_svd_impl(ArenaT& ar, bool dry, const T* M, int64_t m, int64
   const int64_t kcap = have_rmax ? std::min<int64_t>(rmax, L) : L;
   TNB_TRY(eig_carve<TBk>(ar, L, kcap, have_rmax, ew));
   float* Gf = (ew.chfsi && std::is_same<TBk, float>::value) ? reinterpret_cast<float*>(ew.Gb) : nullptr;
-  T* fac = ar.template take<T>((size_t)L * (size_t)kcap);
+  // the factor scratch holds what the eigen stage can return: all L vectors from the direct solver, at most ew.k
+  // from the subspace solver (an eps/delta-only request and the sizing pass then carve the same amount)
+  const int64_t fcap = ew.chfsi ? std::min<int64_t>(L, ew.k) : L;
+  T* fac = ar.template take<T>((size_t)L * (size_t)fcap);
   if (dry) return TNB_OK;
   if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "truncated_svd: workspace too small (need > %zu bytes)", ar.off);
   int* h_sc = static_cast<int*>(pinned_scratch(sizeof(SweepScalars)));
@@ -244,11 +247,11 @@ inline int truncated_svd_impl(ArenaT& ar, bool dry, const T* M, int64_t m, int64
   TNB_LAUNCH_CHECK();
   set_delta2_kernel<<<1, 32, 0, st>>>(sc, delta, eps);
   TNB_LAUNCH_CHECK();
-  TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, sc, h_sc, rmax, 0, nullptr, nullptr, st, false,
-                                  false));
+  TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, sc, h_sc, rmax, batch_mode, nullptr, nullptr,
+                                  st, false, false));
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(h_sc);
-  int64_t r = std::min<int64_t>(hs->rank, kcap);
-  if (hs->zero_flag) {  // round.py:137-145
+  int64_t r = std::min<int64_t>(hs->rank, std::min<int64_t>(kcap, fcap));
+  if (hs->zero_flag && !batch_mode) {  // round.py:137-145
     *rank_host = 1;
     fill_kernel<T><<<grid_for(m), 256, 0, st>>>(left, m, (T)0);
     TNB_LAUNCH_CHECK();
@@ -257,7 +260,9 @@ inline int truncated_svd_impl(ArenaT& ar, bool dry, const T* M, int64_t m, int64
     TNB_CUDA(cudaStreamSynchronize(st));
     return TNB_OK;
   }
-  *rank_host = (int32_t)r;
+  // batch mode: a zero sample keeps rank = min(rmax, len(S)) (its factors come out as zeros); the sign tells the
+  // caller, which returns rank-1 zeros only when EVERY sample of the batch is zero (round.py:138-142)
+  *rank_host = (batch_mode && hs->zero_flag) ? -(int32_t)r : (int32_t)r;
   if (use_left) {
     if (left_ortho) {  // left = U_r ; right = U_r^T M
       scale_extract_kernel<T><<<grid_for(m * r), 256, 0, st>>>(ew.V, ew.ldv, (int)m, (int)r, ew.w, left, 0, 0);

@@ -21,21 +21,38 @@ def shard_range(batch: int, world: int, rank: int):
     return lo, hi
 
 
-def all_gather_cores(local: Sequence[Sequence[torch.Tensor]], batch: int) -> List[List[torch.Tensor]]:
+def _dtype_name(dt):
+    return str(dt).replace("torch.", "")
+
+
+def all_gather_cores(local: Sequence[Sequence[torch.Tensor]], batch: int, device=None) -> List[List[torch.Tensor]]:
     """local: for each locally-owned problem, its list of TT cores.  Returns the cores of all `batch`
-    problems on every rank.  Ranks are data dependent (eps-driven), so shapes are gathered first, then one
-    flat all-gather moves the payload (padded to the largest shard)."""
+    problems on every rank.  Ranks are data dependent (eps-driven), so shapes (and the dtype) are gathered
+    first, then one flat all-gather moves the payload (padded to the largest shard).  A rank that owns no
+    problem (batch < world size) takes the dtype from the gathered metadata and the device from `device`
+    (default: its current CUDA device under NCCL, the CPU under gloo)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [list(c) for c in local]
-    world, rank = dist.get_world_size(), dist.get_rank()
-    dev = local[0][0].device if len(local) else torch.device("cpu")
-    dtype = local[0][0].dtype if len(local) else torch.float32
-    meta = [[list(c.shape) for c in cores] for cores in local]
+    world = dist.get_world_size()
+    meta = dict(shapes=[[list(c.shape) for c in cores] for cores in local],
+                dtype=_dtype_name(local[0][0].dtype) if len(local) else None)
     metas = [None] * world
     dist.all_gather_object(metas, meta)
+    names = {m["dtype"] for m in metas if m["dtype"] is not None}
+    if len(names) > 1:
+        raise ValueError(f"all_gather_cores: ranks hold different dtypes {sorted(names)}")
+    dtype = getattr(torch, names.pop()) if names else torch.float32
+    if len(local):
+        dev = local[0][0].device
+    elif device is not None:
+        dev = torch.device(device)
+    elif dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
     flat = torch.cat([c.reshape(-1) for cores in local for c in cores]) if len(local) else torch.empty(0, dtype=dtype, device=dev)
-    sizes = [sum(int(torch.Size(s).numel()) for cores in m for s in cores) for m in metas]
-    pad = max(sizes) if sizes else 0
+    sizes = [sum(int(torch.Size(s).numel()) for cores in m["shapes"] for s in cores) for m in metas]
+    pad = max(max(sizes) if sizes else 0, 1)
     buf = torch.zeros(pad, dtype=dtype, device=dev)
     buf[: flat.numel()] = flat
     out = [torch.empty(pad, dtype=dtype, device=dev) for _ in range(world)]
@@ -43,7 +60,7 @@ def all_gather_cores(local: Sequence[Sequence[torch.Tensor]], batch: int) -> Lis
     result: List[List[torch.Tensor]] = []
     for g in range(world):
         off = 0
-        for cores in metas[g]:
+        for cores in metas[g]["shapes"]:
             cur = []
             for s in cores:
                 n = int(torch.Size(s).numel())

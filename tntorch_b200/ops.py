@@ -209,8 +209,10 @@ def tt_round(cores: Sequence[torch.Tensor], eps: float = 1e-14, rmax=None, batch
     return res
 
 
-def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=True) -> Tuple[torch.Tensor, torch.Tensor]:
-    """tn.truncated_svd (round.py:52-187), non-batch."""
+def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=True, batch_mode: bool = False,
+                  return_zero_flag: bool = False):
+    """tn.truncated_svd (round.py:52-187) of one matrix.  batch_mode = the reference's rank rule for one sample of a
+    batch (round.py:149-150); return_zero_flag additionally returns whether the sample was numerically zero."""
     if delta is not None and eps is not None:
         raise ValueError("Provide either `delta` or `eps`")
     _require_cuda(M, "truncated_svd")
@@ -235,10 +237,11 @@ def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=T
     rank = (C.c_int32 * 1)()
     with torch.cuda.device(M.device):
         check(L.tnb_truncated_svd(code, _ptr(M), m, n, -1.0 if delta is None else float(delta),
-                                  -1.0 if eps is None else float(eps), rm, 1 if left_ortho else 0, _ptr(ws), ws.numel(),
-                                  _ptr(left), _ptr(right), rank, _stream()))
-    r = rank[0]
-    return left[: m * r].view(m, r), right[: r * n].view(r, n)
+                                  -1.0 if eps is None else float(eps), rm, (1 if left_ortho else 0) | (2 if batch_mode else 0),
+                                  _ptr(ws), ws.numel(), _ptr(left), _ptr(right), rank, _stream()))
+    r = abs(rank[0])
+    out = left[: m * r].view(m, r), right[: r * n].view(r, n)
+    return out + (rank[0] < 0,) if return_zero_flag else out
 
 
 def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, return_info: bool = False):

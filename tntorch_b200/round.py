@@ -47,8 +47,11 @@ def truncated_svd(
     assert algorithm in ("svd", "eig")
     if batch:
         # batch mode ignores eps/delta (round.py:149-150): rank = min(rmax, len(S))
-        outs = [ops.truncated_svd(M[b], rmax=min(rmax or min(M.shape[1:]), min(M.shape[1:])), left_ortho=left_ortho)
+        outs = [ops.truncated_svd(M[b], rmax=rmax, left_ortho=left_ortho, batch_mode=True, return_zero_flag=True)
                 for b in range(M.shape[0])]
+        if all(o[2] for o in outs):  # round.py:138-142: every sample is zero -> rank-1 zero factors
+            return (torch.zeros(M.shape[0], M.shape[1], 1, dtype=M.dtype, device=M.device),
+                    torch.zeros(M.shape[0], 1, M.shape[2], dtype=M.dtype, device=M.device))
         return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
     return ops.truncated_svd(M, delta=delta, eps=eps, rmax=rmax, left_ortho=left_ortho)
 
