@@ -34,6 +34,22 @@ constexpr int CF_THREADS = 128;
 constexpr int CF_MAX_STEPS = 48;
 constexpr int CF_RED_LD = 129;    // odd column stride of the partial-tile buffer: conflict-free both ways
 
+// Device-resident control block of the sync-free subspace eigensolver (chfsi_dev.cuh).  The first three ints are the
+// skip words of common.cuh::tnb_skip.  The Rayleigh-Ritz kernel of stage s writes the degree, the coefficients and the
+// ring position of the NEXT filter here; the filter kernel reads them (nothing about the filter passes through the host).
+struct ChfsiCtrl {
+  int done;        // 1 once the captured energy has converged
+  int error;       // 0 ok, 1 Cholesky breakdown (numerically dependent block), 2 not converged, 3 non-finite values
+  int conv_stage;  // stage at which `done` was raised
+  int outer;       // Rayleigh-Ritz steps completed
+  int products;    // filter products executed
+  int steps;       // degree of the next filter
+  int xin;         // ring buffer holding the input block of the next filter; its result lands in ring[0]
+  int jac_sweeps;  // Jacobi sweeps summed over the Rayleigh-Ritz solves (diagnostic)
+  double prev_cap, prev_delta, trace, cap;
+  float a[48], bc[48], g[48];  // CF_MAX_STEPS
+};
+
 struct ChebFilterParams {
   int n, b;        // G is n x n, blocks are n x b (ld = b)
   int nbox;        // ceil(b / 32)
@@ -45,6 +61,8 @@ struct ChebFilterParams {
   int tmem_cols;
   int dsmem;          // 1: launched as clusters of 8, partial tiles reduced through distributed shared memory
   float* partial;     // dsmem == 0: [slab][q][128][nbox*32] partial tiles in global memory (L2 resident)
+  const ChfsiCtrl* ctrl;  // non-null: steps / coefficients / ring rotation come from the device control block
+  int stage;
 };
 
 inline size_t cheb_filter_smem_bytes(int n, int b) {
@@ -76,6 +94,13 @@ cheb_filter_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
                    const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_y2,
                    const ChebFilterParams p) {
   extern __shared__ unsigned char cf_smem_raw[];
+  int nsteps = p.steps, rot = 0;
+  if (p.ctrl) {  // speculative enqueue: the whole grid leaves at once when the solve has converged or failed
+    if (tnb_skip(&p.ctrl->done, p.stage)) return;
+    nsteps = __ldcg(&p.ctrl->steps);
+    rot = __ldcg(&p.ctrl->xin);
+    if (nsteps < 1 || nsteps > CF_MAX_STEPS) return;
+  }
   const uint32_t raw_addr = smem_u32(cf_smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   unsigned char* g_sm = cf_smem_raw + pad;                                  // ksl/32 chunks x 4 boxes
@@ -124,13 +149,15 @@ cheb_filter_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
   const uint32_t red_addr = smem_u32(red);
   const int row_base = m0 + 16 * (int)q;  // the 16 output rows this CTA reduces and writes
 
-  for (int s = 1; s <= p.steps; ++s) {
+  for (int s = 1; s <= nsteps; ++s) {
     const uint32_t par = (uint32_t)(s - 1) & 1u;
-    const int icur = (s - 1) % 3, iprev = (s + 1) % 3, iout = s % 3;
+    const int icur = (s - 1 + rot) % 3, iprev = (s + 1 + rot) % 3, iout = (s + rot) % 3;
     const float* ycur = p.buf[icur];   // written by other CTAs in earlier steps: read through L2 (__ldcg)
     const float* yprev = p.buf[iprev];
     float* yout = p.buf[iout];
-    const float ca = p.a[s - 1], cb = p.bc[s - 1], cg = p.g[s - 1];
+    const float ca = p.ctrl ? __ldcg(&p.ctrl->a[s - 1]) : p.a[s - 1];
+    const float cb = p.ctrl ? __ldcg(&p.ctrl->bc[s - 1]) : p.bc[s - 1];
+    const float cg = p.ctrl ? __ldcg(&p.ctrl->g[s - 1]) : p.g[s - 1];
     if (tid == 0) {
       asm volatile("fence.proxy.async;" ::: "memory");  // Y_{s-1} was written with generic stores by other CTAs
       const CUtensorMap* tm = icur == 0 ? &tmap_y0 : (icur == 1 ? &tmap_y1 : &tmap_y2);
@@ -253,7 +280,9 @@ inline size_t cheb_filter_workspace_bytes(int n, int b) {
 // Returns TNB_ERR_UNSUPPORTED (without touching the blocks, reason in the last-error string) outside the
 // envelope or when the driver refuses the cooperative launch, so that the caller can run the products one by one.
 inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], int steps, const float* a,
-                           const float* bc, const float* g, void* ws, size_t ws_bytes, cudaStream_t st) {
+                           const float* bc, const float* g, void* ws, size_t ws_bytes, cudaStream_t st,
+                           const ChfsiCtrl* ctrl = nullptr, int stage = 0) {
+  if (ctrl) steps = 1;  // the degree comes from the control block
   if (!tc_path_available() || !cheb_filter_shape_ok(n, b) || steps < 1 || steps > CF_MAX_STEPS ||
       ws_bytes < cheb_filter_workspace_bytes(n, b)) {
     last_error_ref() = "resident filter: shape outside the envelope or workspace too small";
@@ -275,7 +304,9 @@ inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], i
   p.nbox = (b + 31) / 32;
   p.ksl = n / CF_KS;
   p.steps = steps;
-  for (int i = 0; i < steps; ++i) { p.a[i] = a[i]; p.bc[i] = bc[i]; p.g[i] = g[i]; }
+  p.ctrl = ctrl;
+  p.stage = stage;
+  for (int i = 0; i < steps && !ctrl; ++i) { p.a[i] = a[i]; p.bc[i] = bc[i]; p.g[i] = g[i]; }
   for (int i = 0; i < 3; ++i) p.buf[i] = bufs[i];
   p.counter = static_cast<unsigned*>(ws);
   p.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);

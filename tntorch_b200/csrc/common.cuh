@@ -190,6 +190,15 @@ class BigKernelGate {
   int dev_;
 };
 
+// Device-side early exit of kernels that were enqueued speculatively (sync-free solver chains, chfsi_dev.cuh):
+// words[0] = done, words[1] = error, words[2] = stage at which `done` was raised.  A kernel of stage s does nothing
+// when an error was raised or when the chain converged at an earlier stage.
+__device__ __forceinline__ bool tnb_skip(const int* words, int stage) {
+  if (!words) return false;
+  const int done = __ldcg(words), err = __ldcg(words + 1), at = __ldcg(words + 2);
+  return err != 0 || (done != 0 && stage > at);
+}
+
 // Pinned host scratch for reading small results back (ranks, Ritz values).
 inline void* pinned_scratch(size_t bytes) {
   static thread_local void* p = nullptr;

@@ -292,7 +292,7 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
         TNB_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
       }
       // A_n = M P^+  (lstsq, tensor.py:358-360)
-      TNB_TRY(jacobi_eigh(P, R, R, lam, Q, js, jinfo, st));
+      TNB_TRY(jacobi2_eigh(P, R, R, lam, Q, js, jinfo, st));
       pinv_from_eig_kernel<<<grid_for(R * R), 256, 0, st>>>(Q, lam, R, 2.220446049250313e-16 * std::max<int64_t>(R, 1), Pinv);
       TNB_LAUNCH_CHECK();
       convert_kernel<double, T><<<grid_for(R * R), 256, 0, st>>>(Pinv, PinvT, (int64_t)R * R);

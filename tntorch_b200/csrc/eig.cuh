@@ -12,6 +12,7 @@
 #include "gram_tc.cuh"
 #include "cheb_filter.cuh"
 #include "jacobi.cuh"
+#include "jacobi2.cuh"
 #include "small_kernels.cuh"
 
 namespace tnb {
@@ -123,7 +124,7 @@ inline int chfsi_orthonormalize(int n, int b, TB** Xio, TB** Xtmp, ChfsiWork<TB>
                                                          0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
     svqb_prep_kernel<<<1, 1024, 0, st>>>(w.S, b, w.d);
     TNB_LAUNCH_CHECK();
-    TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value));
+    TNB_TRY(jacobi2_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value));
     svqb_finish_kernel<TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.lam, w.d, b,
                                                                      std::is_same<TB, float>::value ? 1e-6 : 1e-13, w.Tm);
     TNB_LAUNCH_CHECK();
@@ -144,7 +145,7 @@ inline int chfsi_rayleigh_ritz(const TB* G, int n, int b, TB** Xio, TB** Xtmp, C
                                                        0.0, nullptr, 0, 0.0, false, (double*)nullptr, 0, st)));
   // fp32 blocks: rotations in fp32 and a loose stop (the Ritz vectors are re-filtered anyway and stored in fp32);
   // fp64 blocks: full accuracy, so that U = M V S^-1 built from the Ritz vectors is orthonormal to working precision
-  TNB_TRY(jacobi_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value,
+  TNB_TRY(jacobi2_eigh(w.S, b, b, w.lam, w.Q, w.jscratch, w.jinfo, st, std::is_same<TB, float>::value,
                       std::is_same<TB, float>::value ? 2e-5 : 0.0));
   convert_kernel<double, TB><<<grid_for((int64_t)b * b), 256, 0, st>>>(w.Q, w.Tm, (int64_t)b * b);
   TNB_LAUNCH_CHECK();

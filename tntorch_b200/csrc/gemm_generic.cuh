@@ -38,6 +38,9 @@ struct GemmArgs {
   // batched accumulation: C = sum_b A_b * B_b with A_b = A + b*batch_stride_a (same K each); split z then owns
   // batches [z*batches_per_split, ...) instead of a K range.  nbatch == 0: plain GEMM.
   int64_t nbatch, batches_per_split, batch_stride_a, batch_stride_b;
+  // speculative enqueue (common.cuh::tnb_skip): nullptr = always run
+  const int* skip_words;
+  int skip_stage;
 };
 
 template <typename TA, typename TB, typename TAcc, typename TC, bool A_KMAJ, bool B_KMAJ, bool DIRECT>
@@ -46,6 +49,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
   __shared__ __align__(16) TAcc Bs[GEMM_BK][GEMM_BN + 4];
   const int tm = blockIdx.x, tn = blockIdx.y, z = blockIdx.z;
   if (p.symmetric && tn < tm) return;
+  if (tnb_skip(p.skip_words, p.skip_stage)) return;
   const int64_t m0 = (int64_t)tm * GEMM_BM, n0 = (int64_t)tn * GEMM_BN;
   int64_t kbeg = (int64_t)z * p.k_per_split;
   int64_t kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
@@ -143,7 +147,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const GemmArgs<
 template <typename TAcc, typename TC, typename TC2>
 __global__ void gemm_finalize_kernel(const TAcc* __restrict__ partial, int splits, int64_t M, int64_t N, TC* C,
                                      int64_t ldc, TAcc alpha, const TC* D, int64_t ldd, TAcc beta, const TC* E,
-                                     int64_t lde, TAcc gamma, int symmetric, TC2* C2, int64_t ldc2) {
+                                     int64_t lde, TAcc gamma, int symmetric, TC2* C2, int64_t ldc2,
+                                     const int* skip_words = nullptr, int skip_stage = 0) {
+  if (tnb_skip(skip_words, skip_stage)) return;
   const int64_t total = M * N;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -230,17 +236,18 @@ template <typename TA, typename TB, typename TAcc, typename TC, typename TC2 = T
 inline int gemm_splitk(const GemmPlan& pl, int64_t M, int64_t N, int64_t K, const TA* A, int64_t lda, bool a_kmaj,
                        const TB* B, int64_t ldb, bool b_kmaj, TAcc* partial, TC* C, int64_t ldc, TAcc alpha,
                        const TC* D, int64_t ldd, TAcc beta, const TC* E, int64_t lde, TAcc gamma, bool symmetric,
-                       TC2* C2, int64_t ldc2, cudaStream_t st) {
+                       TC2* C2, int64_t ldc2, cudaStream_t st, const int* skip_words = nullptr, int skip_stage = 0) {
   if (M <= 0 || N <= 0) return TNB_OK;
   GemmArgs<TA, TB, TAcc, TC> a{};
   a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb;
   a.k_per_split = pl.k_per_split; a.partial = partial;
   a.C = nullptr; a.symmetric = symmetric ? 1 : 0;
+  a.skip_words = skip_words; a.skip_stage = skip_stage;
   TNB_TRY((launch_gemm_tiles<TA, TB, TAcc, TC, false>(a, a_kmaj, b_kmaj, pl.splits, st)));
   const int64_t total = M * N;
   int blocks = (int)(ceil_div<int64_t>(total, 256) < 4096 ? ceil_div<int64_t>(total, 256) : 4096);
   gemm_finalize_kernel<TAcc, TC, TC2><<<blocks, 256, 0, st>>>(partial, pl.splits, M, N, C, ldc, alpha, D, ldd, beta, E,
-                                                              lde, gamma, symmetric ? 1 : 0, C2, ldc2);
+                                                              lde, gamma, symmetric ? 1 : 0, C2, ldc2, skip_words, skip_stage);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
 }

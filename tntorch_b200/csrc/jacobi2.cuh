@@ -1,0 +1,175 @@
+// CUDA side of the two-sided Jacobi eigensolver (jacobi2_core.h): a block-level solve usable inside larger one-CTA
+// kernels (the fused Rayleigh-Ritz step of chfsi_dev.cuh) and a stand-alone kernel with the interface of
+// jacobi_eigh_kernel (jacobi.cuh).  Everything lives in shared memory; one __syncthreads after each of the two phases
+// of a round.  n <= 80 in fp64, n <= 112 in fp32 (four n x (n+1) matrices must fit); larger problems stay on jacobi.cuh.
+#pragma once
+#include "common.cuh"
+#include "jacobi.cuh"
+#include "jacobi2_core.h"
+
+namespace tnb {
+
+constexpr int JAC2_MAX_N_F64 = 80;
+constexpr int JAC2_MAX_N_F32 = 112;
+
+template <typename R>
+__host__ __device__ inline size_t jac2_smem_bytes(int n) {
+  const int np = n + (n & 1), m = np / 2, lds = np + 1;
+  size_t b = (size_t)4 * np * lds * sizeof(R);       // S[2], V[2]
+  b += (size_t)(3 * m + 1) * sizeof(R);              // cs
+  b = (b + 15) / 16 * 16;
+  b += (size_t)(m * (m + 1) / 2 + 8) * sizeof(unsigned short);
+  b = (b + 15) / 16 * 16;
+  b += 4 * sizeof(int);
+  return (b + 15) / 16 * 16;
+}
+
+// Carve the solver state out of a shared-memory region of jac2_smem_bytes<R>(n) bytes (16-byte aligned).
+template <typename R>
+__device__ inline void jac2_carve(unsigned char* smem, int n, R tol, Jac2<R>& J) {
+  const int np = n + (n & 1), m = np / 2, lds = np + 1;
+  R* p = reinterpret_cast<R*>(smem);
+  J.S[0] = p; p += (size_t)np * lds;
+  J.S[1] = p; p += (size_t)np * lds;
+  J.V[0] = p; p += (size_t)np * lds;
+  J.V[1] = p; p += (size_t)np * lds;
+  J.cs = p;
+  size_t off = ((size_t)4 * np * lds + 3 * m + 1) * sizeof(R);
+  off = (off + 15) / 16 * 16;
+  J.blk = reinterpret_cast<unsigned short*>(smem + off);
+  off += (size_t)(m * (m + 1) / 2 + 8) * sizeof(unsigned short);
+  off = (off + 15) / 16 * 16;
+  J.flag = reinterpret_cast<int*>(smem + off);
+  J.np = np;
+  J.m = m;
+  J.lds = lds;
+  J.tol2 = tol * tol;
+  J.big2 = tol;
+  J.floor_abs = sizeof(R) == 8 ? (R)2.3e-16 : (R)1.2e-7;
+}
+
+// Block-level solve: S[0] holds the (scaled, symmetric) matrix, V[0] the identity; on return buffer `cur` (the return
+// value) holds the rotated matrix (diagonal = eigenvalues, unsorted) and the eigenvectors in the columns of V[cur].
+// Every thread of the block must call it.  *sweeps_out (shared or local) receives the number of sweeps.
+template <typename R>
+__device__ inline int jac2_solve(const Jac2<R>& J, int max_sweeps, int* sweeps_out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  jac2_build_blocks(J, tid, nt);
+  const int rounds = J.np > 2 ? J.np - 1 : 1;
+  int cur = 0, sweep = 0;
+  bool conv = false;
+  for (; sweep < max_sweeps && !conv; ++sweep) {
+    __syncthreads();
+    if (tid == 0) J.flag[0] = 0;
+    __syncthreads();
+    for (int r = 0; r < rounds; ++r) {
+      jac2_phase_a(J, cur, tid);
+      __syncthreads();
+      jac2_phase_b(J, cur, tid, nt);
+      __syncthreads();
+      cur ^= 1;
+    }
+    conv = (J.flag[0] == 0);
+  }
+  __syncthreads();
+  if (sweeps_out) *sweeps_out = conv ? sweep : -sweep;
+  return cur;
+}
+
+// Stand-alone eigensolver with the contract of jacobi_eigh_kernel: Gin n x n fp64 (ld ldg), w_out descending,
+// V_out n x n row-major (column j = eigenvector of w_out[j]), info[0] = sweeps (negative: max_sweeps hit).
+// Eigenvalues are Rayleigh quotients v^T G v in fp64 against the input matrix (so the fp32 variant returns values as
+// accurate as its vectors allow, not the rounding-accumulated diagonal).
+template <typename R>
+__global__ void __launch_bounds__(1024) jacobi2_eigh_kernel(const double* __restrict__ Gin, int n, int ldg,
+                                                            double* __restrict__ w_out, double* __restrict__ V_out,
+                                                            int max_sweeps, R tol, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char jac2_smem[];
+  __shared__ double s_w[JAC2_MAX_N + 2];
+  __shared__ int s_rank[JAC2_MAX_N + 2];
+  __shared__ double s_gmax;
+  __shared__ int s_sweeps;
+  Jac2<R> J;
+  jac2_carve<R>(jac2_smem, n, tol, J);
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int np = J.np, lds = J.lds;
+  double dmax = 0.0;
+  for (int i = tid; i < n; i += nt) dmax = fmax(dmax, fabs(Gin[(size_t)i * ldg + i]));
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (tid == 0) s_gmax = 0.0;
+  __syncthreads();
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_gmax), (unsigned long long)__double_as_longlong(dmax));
+  __syncthreads();
+  const double gscale = s_gmax > 0.0 ? s_gmax : 1.0;
+  const double ginv = 1.0 / gscale;
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int r = idx / np, c = idx - r * np;
+    double v = 0.0;
+    if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]) * ginv;
+    J.S[0][r * lds + c] = (R)v;
+    J.V[0][r * lds + c] = (r == c) ? (R)1 : (R)0;
+  }
+  __syncthreads();
+  const int cur = jac2_solve(J, max_sweeps, &s_sweeps);
+  const R* V = J.V[cur];
+  // Rayleigh quotients against the input (fp64), one warp per column; the pad column (odd n) is the one that still
+  // carries the unit entry of the pad row and is ranked last
+  for (int j = warp; j < np; j += nwarps) {
+    double acc = 0.0;
+    for (int r = lane; r < n; r += 32) {
+      double t = 0.0;
+      for (int c = 0; c < n; ++c) t = fma(0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]), (double)V[c * lds + j], t);
+      acc = fma((double)V[r * lds + j], t, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const bool pad = (np != n) && fabs((double)V[n * lds + j]) > 0.5;
+      s_w[j] = pad ? -1e300 : acc;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += nt) {
+    const double wi = s_w[i];
+    int r = 0;
+    for (int j = 0; j < np; ++j) {
+      const double wj = s_w[j];
+      r += (wj > wi) || (wj == wi && j < i);
+    }
+    s_rank[i] = r;
+    if (r < n) w_out[r] = wi;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * np; idx += nt) {
+    const int k = idx / np, i = idx - k * np;
+    const int r = s_rank[i];
+    if (r < n) V_out[(size_t)k * n + r] = (double)V[k * lds + i];
+  }
+  if (tid == 0 && info) info[0] = s_sweeps;
+}
+
+inline bool jacobi2_ok(int n, bool single_precision) {
+  return n >= 1 && n <= (single_precision ? JAC2_MAX_N_F32 : JAC2_MAX_N_F64);
+}
+inline int jacobi2_threads(int n) { return n <= 24 ? 128 : (n <= 40 ? 256 : (n <= 56 ? 512 : 1024)); }
+
+// Same contract as jacobi_eigh (jacobi.cuh); falls back to it outside the shared-memory envelope.
+inline int jacobi2_eigh(const double* G, int n, int ldg, double* w, double* V, double* scratch, int* info, cudaStream_t st,
+                        bool single_precision = false, double loose_tol = 0.0) {
+  static const bool disabled = getenv("TNB_NO_JACOBI2") != nullptr;  // A/B switch (profiling)
+  if (disabled || !jacobi2_ok(n, single_precision)) return jacobi_eigh(G, n, ldg, w, V, scratch, info, st, single_precision, loose_tol);
+  const int max_sweeps = 30;
+  static PerDeviceFlag attr_done[2];
+  if (single_precision) {
+    const float tol = loose_tol > 0.0 ? (float)loose_tol : 2e-6f;
+    TNB_CUDA(ensure_dyn_smem(attr_done[0], jacobi2_eigh_kernel<float>, (int)jac2_smem_bytes<float>(JAC2_MAX_N_F32)));
+    jacobi2_eigh_kernel<float><<<1, jacobi2_threads(n), jac2_smem_bytes<float>(n), st>>>(G, n, ldg, w, V, max_sweeps, tol, info);
+  } else {
+    const double tol = loose_tol > 0.0 ? loose_tol : 1e-14;
+    TNB_CUDA(ensure_dyn_smem(attr_done[1], jacobi2_eigh_kernel<double>, (int)jac2_smem_bytes<double>(JAC2_MAX_N_F64)));
+    jacobi2_eigh_kernel<double><<<1, jacobi2_threads(n), jac2_smem_bytes<double>(n), st>>>(G, n, ldg, w, V, max_sweeps, tol, info);
+  }
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+}  // namespace tnb

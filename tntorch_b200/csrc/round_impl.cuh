@@ -149,7 +149,7 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
         ar.off = mark;
         continue;
       }
-      TNB_TRY(jacobi_eigh(G, (int)cols, (int)cols, w, V, js, jinfo, st));
+      TNB_TRY(jacobi2_eigh(G, (int)cols, (int)cols, w, V, js, jinfo, st));
       const int64_t cap = std::min<int64_t>(rowsA, cols);
       rank_thresh_kernel<<<1, 32, 0, st>>>(w, (int)cols, 64.0 * 2.220446049250313e-16, (int)cap, cx.sc);
       TNB_LAUNCH_CHECK();

@@ -15,8 +15,40 @@ struct SweepScalars {
   int zero_flag;     // 1 when the current unfolding is numerically zero (round.py:137-145)
   int jacobi_info;   // sweeps used by the last Jacobi solve (negative: not converged)
   int undecided;     // leading-values rule only: 1 when the tail behind the kk known values is still above delta^2
-  int spare_i[4];
+  int tf32_reject;   // the Gram matrix of this step came from the TF32 tensor-core kernel and its noise floor could move
+                     // the relative error by more than the parity bar: the step must be redone with the exact Gram
+  int spare_i[3];
 };
+
+// Is a TF32 tensor-core Gram good enough for THIS spectrum?  G_tf32 = (1 - c) G + E with ||E|| ~ 2e-6 ||G||
+// (tests/test_model.py).  The uniform shrink is harmless; E costs captured energy: at most 2 r ||E|| (Ky Fan), and when
+// the kept and discarded parts are separated by gap = lambda_{r-1} - lambda_r, at most lambda_0 r (||E|| / gap)^2
+// (Davis-Kahan).  The step is accepted when that loss moves the relative error sqrt(tail / trace) by less than 5e-6
+// (half the 1e-5 parity bar), with the tail taken at the low end of what the noisy values resolve.  A flat spectrum
+// (random data: lambda_0 << trace, tail ~ trace) passes on the first bound; signal + noise with a clear gap passes on the
+// second; a tensor whose discarded tail is below ~1e-4 of its norm does not, and takes the exact Gram.
+__device__ inline int tf32_gram_rejected(const double* w, int nvals, int L, int rank, double trace) {
+  if (rank >= L) return 0;  // nothing discarded
+  const double lam0 = w[0] > 0.0 ? w[0] : 0.0;
+  if (!(trace > 0.0) || !(lam0 > 0.0)) return 0;
+  const double normE = 4e-6 * lam0;  // twice the measured 2e-6
+  double head = 0.0;
+  for (int i = 0; i < rank && i < nvals; ++i) head += w[i] > 0.0 ? w[i] : 0.0;
+  const double first = 2.0 * rank * normE;
+  const double tail_lo = trace - head - first;
+  if (!(tail_lo > 0.0)) return 1;
+  double loss = first;
+  if (rank < nvals) {
+    const double next = w[rank] > 0.0 ? w[rank] : 0.0;
+    const double gap = w[rank - 1] - next;
+    if (gap > 4.0 * normE) {
+      const double q = normE / gap;
+      const double second = lam0 * rank * q * q;
+      if (second < loss) loss = second;
+    }
+  }
+  return loss > 1e-5 * sqrt(tail_lo * trace) ? 1 : 0;
+}
 
 __global__ void trace_kernel(const double* __restrict__ G, int n, int ld, SweepScalars* sc, int set_norm,
                              double eps_scaled /* (eps/max(1,sqrt(N-1)))^2, used when set_norm */) {
@@ -47,8 +79,9 @@ __global__ void set_delta2_kernel(SweepScalars* sc, double delta_abs, double eps
 //   leading values only (topk == 1): w holds kk >= min(rmax, L) leading Ritz values; the tail energy
 //   behind index k is trace - sum_{i<=k} w_i.
 __global__ void rank_rule_kernel(const double* __restrict__ w, int L, int kk, int rmax, int topk, int batch_mode,
-                                 SweepScalars* sc) {
+                                 SweepScalars* sc, int used_tf32 = 0, int nvals = 0) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  sc->tf32_reject = 0;
   const double w0 = w[0] > 0.0 ? w[0] : 0.0;
   sc->zero_flag = (sqrt(w0) < 1e-13) ? 1 : 0;
   sc->undecided = 0;
@@ -84,6 +117,20 @@ __global__ void rank_rule_kernel(const double* __restrict__ w, int L, int kk, in
   }
   if (rank < 1) rank = 1;
   sc->rank = rank;
+  if (used_tf32 && !sc->zero_flag && !sc->undecided) sc->tf32_reject = tf32_gram_rejected(w, nvals > 0 ? nvals : (topk ? kk : L), L, rank, sc->trace);
+}
+
+// Speculative sweep (sweep.cuh): the step was enqueued assuming rank == expect; record the rank the rule chose and raise
+// the flags the host checks at its single final synchronisation.
+//   bit 0: TF32 Gram rejected   bits 1-3: subspace solver (chfsi_dev.cuh)   bit 4: rank differs   bit 5: zero unfolding
+__global__ void spec_check_kernel(const SweepScalars* sc, int expect, int32_t* rank_out, int* flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *rank_out = sc->rank;
+  int f = 0;
+  if (sc->tf32_reject) f |= 1;
+  if (sc->rank != expect) f |= 16;
+  if (sc->zero_flag) f |= 32;
+  if (f) atomicOr(flags, f);
 }
 
 // out[i][j] (or out[j][i] when transpose) = V[i][j] * f(w_j) for j < rank, i < rows.
@@ -171,10 +218,9 @@ __global__ void svqb_finish_kernel(const double* __restrict__ Q, const double* _
 // A pivot below 1e-11 (numerically dependent columns) raises *flag and is clamped: the caller then
 // falls back to the eigen-decomposition based SVQB transform.
 template <typename TB>
-__global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restrict__ S, int b, double* scratch,
-                                                         TB* __restrict__ T, int* flag, int use_smem,
-                                                         TB* __restrict__ Rout = nullptr) {
-  extern __shared__ __align__(16) unsigned char chol_smem_raw[];
+__device__ __forceinline__ void chol_orth_device(const double* __restrict__ S, int b, double* scratch,
+                                                 TB* __restrict__ T, int* flag, int use_smem, TB* __restrict__ Rout,
+                                                 unsigned char* chol_smem_raw) {
   __shared__ double s_d[JACOBI_MAX_N];
   __shared__ double s_piv[JACOBI_MAX_N];
   const int ld = b | 1;  // odd leading dimension: column walks (stride ld) spread over the banks
@@ -239,6 +285,14 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restric
     // the matching triangular factor R = L^T D^-1 (A = (A T) R): R[i][j] = L[j][i] / d_j
     if (Rout) Rout[idx] = (TB)((j >= i && s_d[j] > 0.0) ? L[(size_t)j * ld + i] / s_d[j] : 0.0);
   }
+}
+
+template <typename TB>
+__global__ void __launch_bounds__(1024) chol_orth_kernel(const double* __restrict__ S, int b, double* scratch,
+                                                         TB* __restrict__ T, int* flag, int use_smem,
+                                                         TB* __restrict__ Rout = nullptr) {
+  extern __shared__ __align__(16) unsigned char chol_smem_dyn[];
+  chol_orth_device<TB>(S, b, scratch, T, flag, use_smem, Rout, chol_smem_dyn);
 }
 
 inline int grid_for(int64_t n, int block = 256, int cap = 4096) {

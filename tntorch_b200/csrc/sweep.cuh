@@ -16,6 +16,7 @@
 #include "eig.cuh"
 #include "gemm_generic.cuh"
 #include "jacobi.cuh"
+#include "jacobi2.cuh"
 #include "small_kernels.cuh"
 #include "gram_tc.cuh"
 #include "gram_tc2.cuh"
@@ -189,7 +190,7 @@ template <typename TBk>
 inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e, const double* d_trace,
                    ChfsiStats* stats, cudaStream_t st, bool allow_tc = false, bool shared_gpu = false, int k_try = 0,
                    double tol = 1e-6) {
-  if (!e.chfsi) return jacobi_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
+  if (!e.chfsi) return jacobi2_eigh(G, (int)L, (int)L, e.w, e.V, e.jscratch, e.jinfo, st);
   e.cw.use_tc = allow_tc;
   e.cw.shared_gpu = shared_gpu;
   e.cw.narrow = shared_gpu && getenv("TNB_NARROW") != nullptr;

@@ -396,7 +396,7 @@ int tnb_eigh_jacobi(const double* G, int32_t n, double* w, double* V, void* work
   double* js = ar.take<double>(jacobi_scratch_doubles(n));
   int* jinfo = ar.take<int>(4);
   if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tnb_eigh_jacobi: workspace too small");
-  return jacobi_eigh(G, n, n, w, V, js, jinfo, as_stream(stream));
+  return jacobi2_eigh(G, n, n, w, V, js, jinfo, as_stream(stream));
 }
 
 size_t tnb_eig_topk_workspace_bytes(int32_t n, int32_t k, int32_t b) {
