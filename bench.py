@@ -4,11 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape 64,64,64,64,64] [--rank 32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" = one complete TT-SVD (tn.Tensor(X, ranks_tt=r)) of one dense fp32 tensor per GPU.
+A "step" = one tnb_ttsvd_batch call per GPU: the complete TT-SVD (tn.Tensor(X[B, ...], ranks_tt=r, batch=True)) of
+--per-gpu-batch dense fp32 tensors.
 Workload: BASELINE.json configs[1] names 64^8 (2^48 elements = 1.1 PB) which cannot exist on any
 machine; the stand-in is the largest 64^d that fits one GPU, randn(64,64,64,64,64) fp32 (4 GiB),
-target TT-rank 32.  Multi-GPU: weak scaling, one tensor per
-rank (the batch dimension shards), no data-path collective, one NCCL all-gather of the final cores.
+target TT-rank 32.  Multi-GPU: weak scaling, the batch dimension
+shards over the ranks, no data-path collective, one NCCL all-gather of the final cores per step.
 """
 import argparse
 import json
@@ -36,12 +37,9 @@ def parse():
     ap.add_argument("--cpu-shape", default="32,32,32,32,32", help="bounded sample timed on the host cores")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (measured: no gain on B200, default 0)")
     ap.add_argument("--per-gpu-batch", type=int, default=6,
-                    help="independent tensors decomposed concurrently per GPU (one CUDA stream + host thread each): the "
-                         "latency-bound eigen phases of one overlap the bandwidth-bound Gram/projection phases of another")
-    ap.add_argument("--step-barrier", action="store_true",
-                    help="join all in-flight tensors after every step instead of once after the K steps")
-    ap.add_argument("--no-concurrent-flag", action="store_true",
-                    help="A/B: do not pass TNB_FLAG_CONCURRENT when several tensors are in flight")
+                    help="independent tensors per GPU and step, decomposed by ONE tnb_ttsvd_batch call (the library keeps "
+                         "them in flight on internal streams: the latency-bound eigen chains of one tensor run beside the "
+                         "bandwidth-bound Gram/projection kernels of another)")
     return ap.parse_args()
 
 
@@ -255,6 +253,26 @@ def algorithmic_bytes(shape, rank, esz=4):
     return total * esz, carries
 
 
+def tf32_peak_tflops(peaks):
+    """Dense TF32 tcgen05 peak: measured on the box by scripts/measure_tf32_peak.py when its result is committed
+    (profiles/r02_tf32_peak.json), else half the measured burst bf16 cuBLAS rate (the kernel is timed alone)."""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r02_tf32_peak.json")))
+        return float(d["tf32_tflops"]), "measured TF32 tcgen05 peak (profiles/r02_tf32_peak.json: " + d.get("how", "") + ")"
+    except Exception:
+        pass
+    return float(peaks.get("bf16_tflops", 1700.0)) / 2, "TF32 dense peak taken as half the measured burst bf16 cuBLAS rate (kernel timed alone)"
+
+
+def ncu_traffic_from_profiles(kind, step):
+    """dram bytes per launch of the dominant kernels, read at run time from the committed ncu summary (never pasted)."""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r02_ncu_traffic.json")))
+        return d.get(f"{kind}{step}")
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -280,68 +298,32 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    bf16_burst = float(peaks.get("bf16_tflops", 1700.0))
 
+    # ---- the batch of this rank: PB independent tensors, decomposed by ONE library call per step (tnb_ttsvd_batch:
+    # ---- the same entry point tn.Tensor(X[B, ...], ranks_tt=r, batch=True) and dist.ttsvd_batch_sharded go through)
     PB = max(1, args.per_gpu_batch)
-    concurrent = PB > 1 and not args.no_concurrent_flag
-    # concurrent mode: gram_tc2 already leaves 4 SMs idle (72 CTA pairs); keep the same 4 free in every whole-GPU kernel
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else (4 if concurrent else 0)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    probe = ops.TTSVDBatchPlan(shape, torch.float32, 1, rmax=args.rank, device=dev, inflight=1, use_tensorcore=not args.no_tc)
+    per_tensor = numel * 4 + probe.per_tensor_bytes + int(probe.cap) * 4
+    del probe
+    PB = max(1, min(PB, int(0.6 * free_b // per_tensor)))  # bounded by free HBM (inputs + workspaces), never grown
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (4 if PB > 1 else 0)
     ops.set_reserved_sms(reserve)
-    Xs, plans, streams = [], [], []
+    Xb = torch.empty((PB,) + shape, device=dev, dtype=torch.float32)  # PB x 4 GiB >> 126 MB L2
     for b in range(PB):
         g = torch.Generator(device=dev).manual_seed(1234 + rank_id * 16 + b)
-        Xs.append(torch.randn(shape, generator=g, device=dev, dtype=torch.float32))  # 4 GiB each >> 126 MB L2
-        plans.append(ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc,
-                                   concurrent=concurrent))
-        streams.append(torch.cuda.Stream(device=dev))
-    X, plan = Xs[0], plans[0]
-    prof_plan = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, profile=True)
-    prof_plan.ws = plan.ws  # share the workspace
-    prof_plan.cores_buf = plan.cores_buf
-    pool = None
-    if PB > 1:
-        from concurrent.futures import ThreadPoolExecutor
-
-        pool = ThreadPoolExecutor(PB)
-
-    def gather_cores(cores_list):
-        if world == 1:
-            return
-        flat = torch.cat([c.reshape(-1) for cores in cores_list for c in cores])
-        out = torch.empty(world * flat.numel(), dtype=flat.dtype, device=dev)
-        dist.all_gather_into_tensor(out, flat)  # the final factor broadcast (north_star)
-
-    def run_many(b, k):
-        """Worker b: k decompositions back to back on its own stream (no barrier between steps)."""
-        torch.cuda.set_device(local)
-        with torch.cuda.stream(streams[b]):
-            for _ in range(k):
-                cores = plans[b].run(Xs[b])
-        return cores
-
-    def run_steps(k):
-        """k steps = k * PB decompositions.  With several tensors in flight the workers stream through their k
-        tensors independently (a step boundary is not a barrier: the eigen chain that ends one tensor overlaps the
-        Gram of the next), joined once at the end; --step-barrier restores a join after every step."""
-        if PB == 1:
-            for _ in range(k):
-                cores_list = [plan.run(X)]
-                gather_cores(cores_list)
-            return cores_list[0]
-        cur = torch.cuda.current_stream()
-        rounds = [1] * k if args.step_barrier else [k]
-        for kk in rounds:
-            for sb in streams:
-                sb.wait_stream(cur)
-            cores_list = list(pool.map(lambda b: run_many(b, kk), range(PB)))  # one host thread per in-flight tensor
-            for sb in streams:
-                cur.wait_stream(sb)
-            for _ in range(kk):  # the final-factor all-gather of each step (the plan buffers hold the last step's cores)
-                gather_cores(cores_list)
-        return cores_list[0]
+        Xb[b].copy_(torch.randn(shape, generator=g, device=dev, dtype=torch.float32))
+    plan = ops.TTSVDBatchPlan(shape, torch.float32, PB, rmax=args.rank, device=dev, inflight=PB, use_tensorcore=not args.no_tc)
+    gather_out = None
+    if world > 1:
+        gather_out = torch.empty(world * plan.cores_buf.numel(), dtype=torch.float32, device=dev)
 
     def step():
-        return run_steps(1)
+        cores_list = plan.run(Xb)
+        if world > 1:  # the final factor broadcast (north_star): one all-gather of every rank's cores
+            dist.all_gather_into_tensor(gather_out, plan.cores_buf.view(-1))
+        return cores_list
 
     def barrier():
         if world > 1:
@@ -359,7 +341,8 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    cores = run_steps(args.steps)
+    for _ in range(args.steps):
+        cores_list = step()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -371,13 +354,32 @@ def run_ours(args):
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * PB * numel / (ms_step * 1e-3) / 1e9
-    ranks = list(plan.ranks)
+    cores = cores_list[0]
+    ranks = [1] + [int(c.shape[2]) for c in cores]
+    spec_accepted = int(sum(plan.spec))
+    X = Xb[0]
 
-    # ---- per-phase device timings (same kernels, CUDA events inside the library, separate short run) ----
+    # ---- one tensor, one call in flight (latency of a single tn.Tensor(X, ranks_tt=r)) + per-phase device timings
+    # ---- (CUDA events inside the library on the launching stream, TNB_FLAG_PROFILE) ----
+    single = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc)
+    single.ws = plan.ws[: single.ws.numel()] if plan.ws.numel() >= single.ws.numel() else single.ws
+    for _ in range(2):
+        single.run(X)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    nsingle = 5
+    for _ in range(nsingle):
+        single.run(X)
+    s1.record()
+    torch.cuda.synchronize()
+    single_ms = s0.elapsed_time(s1) / nsingle
+    prof_plan = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, profile=True)
+    prof_plan.ws = single.ws
+    prof_plan.cores_buf = single.cores_buf
     phase = {"gram_ms": [], "eig_ms": [], "factor_ms": []}
     nprof = 3
     acc = np.zeros(32)
-    prof_plan.run(X)  # untimed: the single-stream schedule uses kernels (resident filter) the concurrent steps did not load yet
+    prof_plan.run(X)
     for _ in range(nprof):
         prof_plan.run(X)
         acc += np.array(list(prof_plan.info))
@@ -387,18 +389,15 @@ def run_ours(args):
         phase["gram_ms"].append(round(float(acc[8 + 3 * s]), 4))
         phase["eig_ms"].append(round(float(acc[9 + 3 * s]), 4))
         phase["factor_ms"].append(round(float(acc[10 + 3 * s]), 4))
-    # dominant kernel = the largest single phase
+    # dominant kernel = the largest single-kernel phase (Gram and projection phases are ONE kernel each; the eigen
+    # phases are chains of small launches and are reported as a share in phases_ms)
     cand = []
     B_alg, carries = algorithmic_bytes(shape, args.rank)
-    rows0 = numel // shape[-1]
-    # the Gram and projection phases are ONE kernel each (gram_tc_kernel / project_f32_kernel); the eigen phases are
-    # chains of ~100 small launches and are reported as a share instead (phases_ms.eig_ms)
     for s in range(nsteps):
         cand.append((phase["gram_ms"][s], f"Gram of step {s}", s, "gram"))
         cand.append((phase["factor_ms"][s], f"project_tc_kernel (3xTF32 projection of step {s})", s, "factor"))
     cand.sort(reverse=True)
     top_ms, top_name, top_s, top_kind = cand[0]
-    # algorithmic work of that phase
     rows = numel // shape[-1]
     r_prev = 1
     dims = []
@@ -408,86 +407,69 @@ def run_ours(args):
         dims.append((rows, cols, r))
         r_prev = r
         rows //= shape[mu - 1]
-    rws, cls, rr = dims[top_s]
-    if top_kind == "gram":
-        if cls <= 512:  # narrow Gram: HBM-bound, one read of the carry
-            roof = {"kernel": "gram_tc_kernel (" + top_name + ")", "bound": "hbm", "achieved": rws * cls * 4 / top_ms / 1e6,
-                    "peak": hbm_peak, "unit": "GB/s", "alg_bytes": rws * cls * 4}
-        else:  # compute-bound symmetric Gram: rows*cols^2 MACs on the upper triangle -> rows*cols*(cols+1) flops
-            fl = rws * cls * (cls + 1)
-            roof = {"kernel": "gram_tc2_kernel, cta_group::2 (" + top_name + ")", "bound": "tensor",
-                    "achieved": fl / top_ms / 1e9, "peak": bf16_sus / 2,
-                    "unit": "TFLOP/s", "alg_flops": fl,
-                    "peak_note": "TF32 dense peak taken as half the measured sustained bf16 cuBLAS rate (no TF32 entry in MEASURED_PEAKS.json)"}
-    elif top_kind == "factor":
-        by = (rws * cls + rws * rr) * 4
-        roof = {"kernel": top_name, "bound": "hbm", "achieved": by / top_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                "alg_bytes": by}
-    else:
-        by = cls * cls * 4
-        roof = {"kernel": top_name, "bound": "hbm", "achieved": by / top_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                "alg_bytes": by, "note": "latency-bound subspace eigensolver (dependent chain of small GEMMs)"}
+    tf32_peak = tf32_peak_tflops(peaks)
+    tf32_note = tf32_peak[1]
+    tf32_peak = tf32_peak[0]
+
+    def kernel_roof(ms_k, name_k, s_k, kind_k):
+        rws_k, cls_k, rr_k = dims[s_k]
+        if kind_k == "gram" and cls_k > 512:  # compute-bound symmetric Gram: rows*cols*(cols+1) flops on the upper triangle
+            fl = rws_k * cls_k * (cls_k + 1)
+            return {"kernel": "gram_tc2_kernel, cta_group::2 (" + name_k + ")", "bound": "tensor", "achieved": fl / ms_k / 1e9,
+                    "peak": tf32_peak, "unit": "TFLOP/s", "alg_flops": fl, "peak_note": tf32_note, "ms": ms_k}
+        by = rws_k * cls_k * 4 + (rws_k * rr_k * 4 if kind_k == "factor" else 0)
+        return {"kernel": ("gram_tc_kernel (" + name_k + ")") if kind_k == "gram" else name_k, "bound": "hbm",
+                "achieved": by / ms_k / 1e6, "peak": hbm_peak, "unit": "GB/s", "alg_bytes": by, "ms": ms_k}
+
+    roof = kernel_roof(top_ms, top_name, top_s, top_kind)
     roof["frac"] = roof["achieved"] / roof["peak"]
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_summaries.md) for the default 64^5 / r=32 workload; null for other shapes
-    roof["traffic"] = None
-    if list(shape) == [64] * 5 and args.rank == 32 and not args.no_tc:
-        ncu_traffic = {("gram", 0): 4.295e9 + 0.004e9, ("factor", 0): 4.296e9 + 2.109e9, ("gram", 1): 4.185e9 + 0.008e9}
-        roof["traffic"] = ncu_traffic.get((top_kind, top_s))
-        roof["traffic_source"] = "profiles/r01_ncu_summaries.md (ncu --set full, per launch)"
-    roof["ms"] = top_ms
+    roof["traffic"] = ncu_traffic_from_profiles(top_kind, top_s) if list(shape) == [64] * 5 and args.rank == 32 and not args.no_tc else None
+    roof["traffic_source"] = "profiles/r02_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if roof["traffic"] else None
     roof["peak_source"] = peak_src
-    # the other single-kernel phases against their own bound (same CUDA-event timings), largest first
     others = []
     for ms_k, name_k, s_k, kind_k in cand[:4]:
-        rws_k, cls_k, rr_k = dims[s_k]
-        if kind_k == "gram" and cls_k > 512:
-            others.append({"kernel": "gram_tc2_kernel " + name_k, "ms": ms_k, "bound": "tensor",
-                           "frac": rws_k * cls_k * (cls_k + 1) / ms_k / 1e9 / (bf16_sus / 2)})
-        else:
-            by_k = rws_k * cls_k * 4 + (rws_k * rr_k * 4 if kind_k == "factor" else 0)
-            others.append({"kernel": ("gram_tc_kernel " if kind_k == "gram" else "") + name_k, "ms": ms_k, "bound": "hbm",
-                           "frac": by_k / ms_k / 1e6 / hbm_peak})
+        o = kernel_roof(ms_k, name_k, s_k, kind_k)
+        others.append({"kernel": o["kernel"], "ms": ms_k, "bound": o["bound"], "frac": o["achieved"] / o["peak"]})
     roof["kernels"] = others
     sweep_roof = {"alg_bytes_per_tensor": B_alg, "achieved_GBps": PB * B_alg / ms_step / 1e6, "peak_GBps": hbm_peak,
-                  "frac": PB * B_alg / ms_step / 1e6 / hbm_peak}
+                  "frac": PB * B_alg / ms_step / 1e6 / hbm_peak,
+                  "single_call_ms": single_ms, "single_call_GElements_per_s": numel / single_ms / 1e6,
+                  "single_call_frac": B_alg / single_ms / 1e6 / hbm_peak}
 
     # ---- parity of what was just timed (device-side fp64 error kernel; not in the timed region) ----
     relerr = ops.tt_relative_error(X, cores)
+    # the structured twin (random Gaussian data is incompressible, its error says little): a random
+    # TT-rank-32 tensor of the same shape + 1e-2 relative noise, built on the device, decomposed by the same call
+    relerr_twin = None
+    if rank_id == 0 and len(shape) >= 3:
+        gt = torch.Generator(device=dev).manual_seed(99)
+        rk = [1] + [min(args.rank, 32)] * (len(shape) - 1) + [1]
+        f = torch.ones(1, 1, device=dev)
+        for k, sk in enumerate(shape):
+            ck = torch.randn(rk[k], sk * rk[k + 1], generator=gt, device=dev)
+            f = (f @ ck).reshape(-1, rk[k + 1])
+        tw = f.reshape(shape)
+        tw.add_(torch.randn(shape, generator=gt, device=dev), alpha=1e-2 * float(tw.std()))
+        ctw = single.run(tw)
+        relerr_twin = {"value": ops.tt_relative_error(tw, ctw), "noise": 1e-2,
+                       "note": "same call on randn TT-rank-32 signal + 1e-2 sigma noise; reference on the NumPy twin of this "
+                               "construction: 0.01022974 (tests/golden/full.npz, tests/test_gpu_fullgolden.py)"}
+        del tw, f
+    del prof_plan, single
 
-    # ---- e2e: host buffers through the public plan API, H2D + D2H inside the timed region ----
+    # ---- e2e: HOST buffers through the same batch entry point, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        del prof_plan
-        # two host-buffer pipelines per GPU: the H2D copy of one tensor overlaps the kernels of the other (the PCIe
-        # link is the bound: 4 GiB per tensor); every step still moves its own input and its own result
-        EB = 2 if PB > 1 else 1
-        hplans, Xhs = [], []
-        for b in range(EB):
-            hp = ops.TTSVDPlan(shape, torch.float32, rmax=args.rank, device=dev, use_tensorcore=not args.no_tc, host_io=True)
-            hp.ws = plans[b % PB].ws
-            hp.cores_buf = plans[b % PB].cores_buf
-            hplans.append(hp)
-            xh = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-            xh.copy_(Xs[b % PB])
-            Xhs.append(xh)
-
-        def run_host_one(b):
-            torch.cuda.set_device(local)
-            with torch.cuda.stream(streams[b]):
-                hc = hplans[b].run_host(Xhs[b])
-                return float(hc[0][0, 0, 0])  # the result is on the host
+        EB = min(PB, 2)  # two tensors per step: 8 GiB of pinned host memory per rank is enough to be PCIe-bound
+        hplan = ops.TTSVDBatchPlan(shape, torch.float32, EB, rmax=args.rank, device=dev, inflight=EB,
+                                   use_tensorcore=not args.no_tc, host_io=True)
+        hplan.ws = plan.ws  # share the workspace (EB <= PB slices)
+        xh = torch.empty((EB,) + shape, dtype=torch.float32, pin_memory=True)
+        xh.copy_(Xb[:EB])
 
         def e2e_step():
-            if EB == 1:
-                return [run_host_one(0)]
-            cur = torch.cuda.current_stream()
-            for sb in streams[:EB]:
-                sb.wait_stream(cur)
-            r = list(pool.map(run_host_one, range(EB)))
-            for sb in streams[:EB]:
-                cur.wait_stream(sb)
-            return r
+            hc = hplan.run_host(xh)
+            return float(hc[0][0][0, 0, 0])  # the result is on the host
 
         for _ in range(2):
             e2e_step()
@@ -504,8 +486,11 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ems = float(tt.item()) / ksteps
         e2e = {"value": world * EB * numel / (ems * 1e-3) / 1e9, "unit": "GElements/s", "ms_per_step": ems,
-               "h2d_bytes_per_step": EB * numel * 4, "d2h_bytes_per_step": EB * int(hplans[0].cap) * 4, "steps": ksteps,
-               "tensors_per_step": EB}
+               "h2d_bytes_per_step": EB * numel * 4, "d2h_bytes_per_step": EB * int(hplan.cap) * 4, "steps": ksteps,
+               "tensors_per_step": EB,
+               "note": "pinned host tensors -> tnb_ttsvd_batch -> cores in pinned host memory; bound by the PCIe link (4 GiB per tensor)"}
+        del hplan, xh
+        torch.cuda.empty_cache()
 
     cpu = None
     same_sample = None
@@ -559,13 +544,12 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 (Gram: tcgen05 kind::tf32, fp32 TMEM accumulation; projections: 3xTF32 on tcgen05 = fp32 accuracy; Gram matrices, eigenproblems and rank rule in fp64)"
             if not args.no_tc else "f32 (fp64-accumulated Gram, fp32 projections)",
             "data": "synthetic",
-            "config": {"workload": f"TT-SVD randn{list(shape)} fp32 -> TT-rank {args.rank} (stand-in for the infeasible 64^8: 1.1 PB)",
-                       "per_gpu_batch": PB, "in_flight_per_gpu": PB, "reserved_sms": reserve,
-                       "step_join": "every step" if (args.step_barrier or PB == 1) else "once after the K steps (workers stream)",
-                       "concurrent_flag": bool(concurrent),
-                       "parallelism": f"batch-sharded x{world} ({PB} independent tensors in flight per GPU on {PB} streams), all-gather of final cores",
-                       "l2": "input 4 GiB >> 126 MB L2 (no flush needed)", "ranks": ranks},
+            "config": workload_config(args),
+            "run": {"per_gpu_batch_used": PB, "reserved_sms": reserve, "ranks": ranks,
+                    "entry_point": "tnb_ttsvd_batch (ops.TTSVDBatchPlan.run): one call per step and GPU, one host thread, one synchronisation",
+                    "speculative_sweeps_accepted": spec_accepted, "world": world},
             "rel_error": relerr,
+            "rel_error_twin": relerr_twin,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

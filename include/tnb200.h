@@ -45,6 +45,10 @@ extern "C" {
                                     whole-GPU kernels (tensor-core Gram, projection) of all of them are chained
                                     one at a time and sized to leave tnb_set_reserved_sms() SMs free for the
                                     one-CTA eigen kernels of the others                                       */
+#define TNB_FLAG_NO_SPECULATE 16u /* always take the host-driven sweep (one synchronisation per step).  By default a
+                                    decomposition whose ranks are decided by rank caps is enqueued in one go with a
+                                    single synchronisation at the end, and repeated on the host-driven path only if
+                                    the device-side rank rule disagrees (info_host[26], [27])                  */
 
 int tnb_version(void);
 const char* tnb_last_error(void);
@@ -69,7 +73,10 @@ int tnb_has_tensorcore_path(void);
  *   ranks_host ndim+1 ints (host), ranks_host[0] = ranks_host[ndim] = 1
  *   info_host  optional (may be NULL) 32 doubles: [0]=||T||_F, [1]=#eig solves, [2]=#ChFSI matrix products,
  *              [3]=#tensor-core Gram launches; with TNB_FLAG_PROFILE also [4]=Gram ms, [5]=eigen ms,
- *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 7;
+ *              [6]=factor/projection ms (totals), [7]=#steps, [8+3t..10+3t]=the same three for step t < 6;
+ *              [26]=1 when the speculative (single-synchronisation) sweep was accepted, [27]=the device flags that
+ *              made a speculative sweep repeat on the host-driven path (bit 0 TF32 Gram too coarse, bits 1-3 subspace
+ *              solver, bit 4 rank below the cap, bit 5 zero unfolding);
  *              [29]=Jacobi sweeps summed over the Rayleigh-Ritz solves, [30]=#outer subspace iterations,
  *              [31]=#Chebyshev filters that ran as one resident cluster kernel
  * ------------------------------------------------------------------------------------------ */
@@ -78,6 +85,31 @@ size_t tnb_ttsvd_workspace_bytes(int dtype, int ndim, const int64_t* shape, cons
 int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
               uint32_t flags, void* workspace, size_t workspace_bytes, void* cores, int64_t cores_capacity,
               int32_t* ranks_host, double* info_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A batch of dense tensors of ONE shape -> their TT cores.
+ * Replaces: tn.Tensor(data[B, ...], ranks_tt=..., batch=True)  tensor.py:401-408 with the leading batch dimension
+ *           (_full_rank_tt tensor.py:58-104 batch branch + round_tt), and any caller that decomposes many tensors
+ *           (north_star: "batched decompositions shard the batch dimension"; dist.py shards the batch over GPUs and
+ *           calls this per rank).
+ *   data[i] / cores[i]  device pointers of tensor i and of its cores buffer (cores_capacity elements each, layout as
+ *                       in tnb_ttsvd); ranks_host: batch * (ndim + 1) ints
+ *   workspace           k * per_tensor_bytes with k >= 1: up to min(k, 8) decompositions are in flight at once on
+ *                       internal streams, enqueued from the calling thread phase by phase (all Gram kernels of a step,
+ *                       then every tensor's eigen chain + projection) and synchronised ONCE; `stream` is forked from
+ *                       and joined to.  tnb_ttsvd_batch_workspace_bytes() returns the recommended size (6 in flight)
+ *                       and, through per_tensor_bytes, the unit.
+ *   norms_host          optional, batch doubles: ||T_i||_F
+ *   speculative_host    optional, batch ints: 1 if tensor i was accepted from the single-synchronisation sweep
+ * Tensors need rank caps on every bond for the in-flight path (see TNB_FLAG_NO_SPECULATE); otherwise, and for tensors
+ * whose speculation the device rejected, the decomposition runs one tensor at a time like tnb_ttsvd.
+ * ------------------------------------------------------------------------------------------ */
+size_t tnb_ttsvd_batch_workspace_bytes(int dtype, int batch, int ndim, const int64_t* shape, const int32_t* rmax,
+                                       uint32_t flags, size_t* per_tensor_bytes);
+int tnb_ttsvd_batch(int dtype, const void* const* data, int batch, int ndim, const int64_t* shape, const int32_t* rmax,
+                    double eps, uint32_t flags, void* workspace, size_t workspace_bytes, void* const* cores,
+                    int64_t cores_capacity, int32_t* ranks_host, double* norms_host, int32_t* speculative_host,
+                    void* stream);
 
 /* Same, but `data_host` / `cores_host` are HOST buffers (pinned for full speed): the H2D copy is
  * chunked and overlapped with the first Gram pass, cores are copied back before returning.

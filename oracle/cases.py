@@ -269,3 +269,10 @@ FULL_CP_CASES = {
     # BASELINE configs[3] at the CPU-feasible size of BASELINE.md §4: R=50 on 64^4, fp64 oracle, 10 sweeps
     "cp_64x4_R50": dict(shape=(64,) * 4, Rtrue=50, R=50, sweeps=10, noise=1e-2, seed=150, dtype="float64"),
 }
+
+# ---- fp32 inputs whose discarded tail is far below the TF32 noise floor of a tensor-core Gram: the sweep must
+# ---- notice and take the exact Gram; rows >= 2048 at the first steps so that the tensor-core path is the default ----------
+LOWNOISE_CASES = {
+    "twin_lownoise_16x5_f32": dict(kind="tt_noise", shape=(16,) * 5, rank=6, noise=1e-5, seed=31, dtype="float32", ranks_tt=6),
+    "smooth_24x4_f32_r5": dict(kind="smooth", shape=(24, 24, 24, 24), dtype="float32", ranks_tt=5),
+}

@@ -61,6 +61,19 @@ def gen_ttsvd():
     np.savez_compressed(os.path.join(OUT, "ttsvd.npz"), **out)
 
 
+def gen_lownoise():
+    """fp32 inputs with a discarded tail far below the TF32 noise floor (oracle/cases.py LOWNOISE_CASES)."""
+    out = {}
+    for name, spec in cases.LOWNOISE_CASES.items():
+        X = cases.make_dense(spec)
+        for alg in ("svd", "eig"):
+            t = tn.Tensor(torch.as_tensor(X), ranks_tt=spec["ranks_tt"], algorithm=alg)
+            out[f"{name}/{alg}/ranks"] = np.asarray(t.ranks_tt, dtype=np.int64)
+            out[f"{name}/{alg}/relerr"] = np.float64(rel_err64(X, t))
+            print(name, alg, list(t.ranks_tt), out[f"{name}/{alg}/relerr"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "lownoise.npz"), **out)
+
+
 def gen_round():
     out = {}
     for name, spec in cases.ROUND_CASES.items():
@@ -183,9 +196,11 @@ def gen_cross():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross", "tucker"]
+    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross", "tucker", "lownoise"]
     if "ttsvd" in which:
         gen_ttsvd()
+    if "lownoise" in which:
+        gen_lownoise()
     if "round" in which:
         gen_round()
     if "tsvd" in which:

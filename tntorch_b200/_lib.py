@@ -17,6 +17,7 @@ FLAG_NO_TENSORCORE = 1
 FLAG_BATCH_MODE = 2
 FLAG_PROFILE = 4
 FLAG_CONCURRENT = 8
+FLAG_NO_SPECULATE = 16
 
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_NOCONV = 1, 2, 3, 4, 5
 
@@ -43,6 +44,9 @@ SIGNATURES = {
     "tnb_ttsvd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, _i32p, C.c_uint32]),
     "tnb_ttsvd": (C.c_int, [C.c_int, _vp, C.c_int, _i64p, _i32p, C.c_double, C.c_uint32, _vp, C.c_size_t, _vp,
                             C.c_int64, _i32p, _f64p, _vp]),
+    "tnb_ttsvd_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _i64p, _i32p, C.c_uint32, C.POINTER(C.c_size_t)]),
+    "tnb_ttsvd_batch": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, C.c_int, _i64p, _i32p, C.c_double, C.c_uint32, _vp,
+                                  C.c_size_t, C.POINTER(_vp), C.c_int64, _i32p, _f64p, _i32p, _vp]),
     "tnb_ttsvd_host": (C.c_int, [C.c_int, _vp, C.c_int, _i64p, _i32p, C.c_double, C.c_uint32, _vp, _vp, C.c_size_t,
                                  _vp, C.c_int64, _vp, _i32p, _f64p, _vp]),
     "tnb_tt_round_cores_capacity": (C.c_int64, [C.c_int, _i64p, _i32p, _i32p, _i64p]),

@@ -14,11 +14,9 @@ constexpr int JAC2_MAX_N_F32 = 112;
 
 template <typename R>
 __host__ __device__ inline size_t jac2_smem_bytes(int n) {
-  const int np = n + (n & 1), m = np / 2, lds = np + 1;
+  const int np = n + (n & 1), m = np / 2, lds = np + 2;
   size_t b = (size_t)4 * np * lds * sizeof(R);       // S[2], V[2]
-  b += (size_t)(3 * m + 1) * sizeof(R);              // cs
-  b = (b + 15) / 16 * 16;
-  b += (size_t)(m * (m + 1) / 2 + 8) * sizeof(unsigned short);
+  b += (size_t)(4 * m + 4) * sizeof(R);              // cs[2]
   b = (b + 15) / 16 * 16;
   b += 4 * sizeof(int);
   return (b + 15) / 16 * 16;
@@ -27,17 +25,15 @@ __host__ __device__ inline size_t jac2_smem_bytes(int n) {
 // Carve the solver state out of a shared-memory region of jac2_smem_bytes<R>(n) bytes (16-byte aligned).
 template <typename R>
 __device__ inline void jac2_carve(unsigned char* smem, int n, R tol, Jac2<R>& J) {
-  const int np = n + (n & 1), m = np / 2, lds = np + 1;
+  const int np = n + (n & 1), m = np / 2, lds = np + 2;  // even row stride: the 2-element reads are aligned
   R* p = reinterpret_cast<R*>(smem);
   J.S[0] = p; p += (size_t)np * lds;
   J.S[1] = p; p += (size_t)np * lds;
   J.V[0] = p; p += (size_t)np * lds;
   J.V[1] = p; p += (size_t)np * lds;
-  J.cs = p;
-  size_t off = ((size_t)4 * np * lds + 3 * m + 1) * sizeof(R);
-  off = (off + 15) / 16 * 16;
-  J.blk = reinterpret_cast<unsigned short*>(smem + off);
-  off += (size_t)(m * (m + 1) / 2 + 8) * sizeof(unsigned short);
+  J.cs[0] = p; p += 2 * m + 2;
+  J.cs[1] = p;
+  size_t off = ((size_t)4 * np * lds + 4 * m + 4) * sizeof(R);
   off = (off + 15) / 16 * 16;
   J.flag = reinterpret_cast<int*>(smem + off);
   J.np = np;
@@ -48,28 +44,70 @@ __device__ inline void jac2_carve(unsigned char* smem, int n, R tol, Jac2<R>& J)
   J.floor_abs = sizeof(R) == 8 ? (R)2.3e-16 : (R)1.2e-7;
 }
 
-// Block-level solve: S[0] holds the (scaled, symmetric) matrix, V[0] the identity; on return buffer `cur` (the return
+// Block-level solve.  On entry S[0] holds the (scaled) matrix in canonical upper storage — element (i, j), i <= j, at
+// [i * lds + j]; the strict lower triangle is never read — and V[0] the identity.  On return buffer `cur` (the return
 // value) holds the rotated matrix (diagonal = eigenvalues, unsorted) and the eigenvectors in the columns of V[cur].
-// Every thread of the block must call it.  *sweeps_out (shared or local) receives the number of sweeps.
+// Every thread of the block must call it.  Thread roles: the first ceil(m/32) warps are "pair threads" (thread k forms
+// the next round's pair k and its rotation), the others are workers with up to JAC2_ITEMS static work items each in
+// registers (when the block is too small for that, the items are regenerated every round: correct, slower).
 template <typename R>
-__device__ inline int jac2_solve(const Jac2<R>& J, int max_sweeps, int* sweeps_out) {
+__device__ inline int jac2_solve(const Jac2<R>& Jin, int max_sweeps, int* sweeps_out) {
+  const Jac2<R> J = Jin;
   const int tid = threadIdx.x, nt = blockDim.x;
-  jac2_build_blocks(J, tid, nt);
+  const int m = J.m;
+  const int pw = (m + 31) / 32 * 32;
+  const int workers = nt - pw;
+  const int total = jac2_total_items(J);
+  const bool in_regs = total <= workers * JAC2_ITEMS;
+  const int per = (total + workers - 1) / workers;
+  const bool is_pair = tid < m, is_worker = tid >= pw;
+  const int wid = tid - pw;
+  Jac2Item it0, it1, it2;
+  Jac2Pair pp;
+  it0.kind = it1.kind = it2.kind = 0;
+  if (is_worker && in_regs) {
+    jac2_make_item(J, wid, it0);
+    jac2_make_item(J, wid + workers, it1);
+    jac2_make_item(J, wid + 2 * workers, it2);
+  }
+  if (is_pair) jac2_make_pair(J, tid, pp);
+  if (tid == 0) { J.flag[0] = 0; J.flag[1] = 0; }
+  __syncthreads();
+  if (is_pair) jac2_first_pair(J, 0, 0, tid, &J.flag[0]);
+  __syncthreads();
   const int rounds = J.np > 2 ? J.np - 1 : 1;
+  // explicit buffer pointers swapped in registers (no dynamically indexed arrays in the round loop)
+  R *Sr = J.S[0], *Sw = J.S[1], *Vr = J.V[0], *Vw = J.V[1], *cr = J.cs[0], *cw = J.cs[1];
   int cur = 0, sweep = 0;
   bool conv = false;
   for (; sweep < max_sweeps && !conv; ++sweep) {
-    __syncthreads();
-    if (tid == 0) J.flag[0] = 0;
-    __syncthreads();
+    int* fl = &J.flag[sweep & 1];
+    if (tid == 0) J.flag[(sweep + 1) & 1] = 0;  // nobody touches the other flag during this sweep
     for (int r = 0; r < rounds; ++r) {
-      jac2_phase_a(J, cur, tid);
-      __syncthreads();
-      jac2_phase_b(J, cur, tid, nt);
+      Jac2<R> Jc = J;  // read side at index 0, write side at index 1
+      Jc.S[0] = Sr; Jc.S[1] = Sw; Jc.V[0] = Vr; Jc.V[1] = Vw; Jc.cs[0] = cr; Jc.cs[1] = cw;
+      if (is_worker) {
+        if (in_regs) {
+          jac2_do_item(Jc, 0, 0, it0);
+          jac2_do_item(Jc, 0, 0, it1);
+          jac2_do_item(Jc, 0, 0, it2);
+        } else {
+          for (int q = 0; q < per; ++q) {
+            Jac2Item it;
+            jac2_make_item(J, wid + q * workers, it);
+            jac2_do_item(Jc, 0, 0, it);
+          }
+        }
+      } else if (is_pair) {
+        jac2_do_pair(Jc, 0, 0, tid, pp, fl);
+      }
       __syncthreads();
       cur ^= 1;
+      { R* t = Sr; Sr = Sw; Sw = t; }
+      { R* t = Vr; Vr = Vw; Vw = t; }
+      { R* t = cr; cr = cw; cw = t; }
     }
-    conv = (J.flag[0] == 0);
+    conv = (*fl == 0);
   }
   __syncthreads();
   if (sweeps_out) *sweeps_out = conv ? sweep : -sweep;
@@ -106,19 +144,40 @@ __global__ void __launch_bounds__(1024) jacobi2_eigh_kernel(const double* __rest
     const int r = idx / np, c = idx - r * np;
     double v = 0.0;
     if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]) * ginv;
-    J.S[0][r * lds + c] = (R)v;
+    if (c >= r) J.S[0][r * lds + c] = (R)v;  // canonical upper storage
     J.V[0][r * lds + c] = (r == c) ? (R)1 : (R)0;
   }
   __syncthreads();
   const int cur = jac2_solve(J, max_sweeps, &s_sweeps);
   const R* V = J.V[cur];
+  if (sizeof(R) == 4) {
+    // ~500 fp32 rotations per column leave V orthogonal to ~1e-5; one Newton-Schulz step V <- V (1.5 I - 0.5 V^T V)
+    // in fp32 brings that to ~1e-7, the level of the fp32 factors extracted from it
+    R* E = J.S[0];
+    R* Vn = J.V[cur ^ 1];
+    for (int idx = tid; idx < np * np; idx += nt) {
+      const int i = idx / np, j = idx - i * np;
+      R acc = (R)0;
+      for (int c = 0; c < np; ++c) acc = fma(V[c * lds + i], V[c * lds + j], acc);
+      E[i * lds + j] = (i == j ? (R)1.5 : (R)0) - (R)0.5 * acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < np * np; idx += nt) {
+      const int i = idx / np, j = idx - i * np;
+      R acc = (R)0;
+      for (int c = 0; c < np; ++c) acc = fma(V[i * lds + c], E[c * lds + j], acc);
+      Vn[i * lds + j] = acc;
+    }
+    __syncthreads();
+    V = Vn;
+  }
   // Rayleigh quotients against the input (fp64), one warp per column; the pad column (odd n) is the one that still
   // carries the unit entry of the pad row and is ranked last
   for (int j = warp; j < np; j += nwarps) {
     double acc = 0.0;
     for (int r = lane; r < n; r += 32) {
       double t = 0.0;
-      for (int c = 0; c < n; ++c) t = fma(0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]), (double)V[c * lds + j], t);
+      for (int c = 0; c < n; ++c) t = fma(Gin[(size_t)c * ldg + r], (double)V[c * lds + j], t);  // G symmetric: coalesced side
       acc = fma((double)V[r * lds + j], t, acc);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -150,7 +209,17 @@ __global__ void __launch_bounds__(1024) jacobi2_eigh_kernel(const double* __rest
 inline bool jacobi2_ok(int n, bool single_precision) {
   return n >= 1 && n <= (single_precision ? JAC2_MAX_N_F32 : JAC2_MAX_N_F64);
 }
-inline int jacobi2_threads(int n) { return n <= 24 ? 128 : (n <= 40 ? 256 : (n <= 56 ? 512 : 1024)); }
+// pair warps + enough workers for JAC2_ITEMS items each (rounded to warps)
+inline int jacobi2_threads(int n) {
+  const int np = n + (n & 1), m = np / 2;
+  const int pw = (m + 31) / 32 * 32;
+  const int total = m * (m + 1) / 2 + np * m;
+  int w = (total + JAC2_ITEMS - 1) / JAC2_ITEMS;
+  w = (w + 31) / 32 * 32;
+  int t = pw + w;
+  if (t < 64) t = 64;
+  return t > 1024 ? 1024 : t;
+}
 
 // Same contract as jacobi_eigh (jacobi.cuh); falls back to it outside the shared-memory envelope.
 inline int jacobi2_eigh(const double* G, int n, int ldg, double* w, double* V, double* scratch, int* info, cudaStream_t st,

@@ -22,6 +22,7 @@
 #include "gram_tc2.cuh"
 #include "project.cuh"
 #include "project_tc.cuh"
+#include "chfsi_dev.cuh"
 
 namespace tnb {
 
@@ -209,7 +210,7 @@ inline int eig_run(const double* G, const TBk* Gb_in, int64_t L, EigWork<TBk>& e
 template <typename TBk>
 inline int eig_solve_and_rank(const double* G, const TBk* Gb, int64_t L, EigWork<TBk>& ew, SweepScalars* sc, int* h_sc,
                               int32_t rm, int batch_mode, ChfsiStats* total, int* solves, cudaStream_t st, bool allow_tc,
-                              bool shared_gpu) {
+                              bool shared_gpu, int used_tf32 = 0) {
   const SweepScalars* hs = reinterpret_cast<const SweepScalars*>(h_sc);
   const bool adaptive = ew.chfsi && ew.adaptive;
   int k_try = adaptive ? 32 : 0;
@@ -227,7 +228,8 @@ inline int eig_solve_and_rank(const double* G, const TBk* Gb, int64_t L, EigWork
       total->products += cs.products, total->fused_filters += cs.fused_filters, total->outer += cs.outer,
           total->rr_sweeps += cs.rr_sweeps;
     if (solves) *solves += 1;
-    rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.k_run : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, sc);
+    rank_rule_kernel<<<1, 32, 0, st>>>(ew.w, (int)L, ew.chfsi ? ew.k_run : (int)L, rm, ew.chfsi ? 1 : 0, batch_mode, sc,
+                                       used_tf32, ew.chfsi ? ew.b_run : (int)L);
     TNB_LAUNCH_CHECK();
     TNB_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
     TNB_CUDA(cudaStreamSynchronize(st));
@@ -253,6 +255,8 @@ struct SweepInfo {
   int fused_filters = 0;  // Chebyshev filters run as one resident kernel (cheb_filter.cuh)
   int rr_sweeps = 0, rr_solves = 0;  // Jacobi sweeps / solves of the Rayleigh-Ritz steps (diagnostic)
   int tc_grams = 0;
+  int speculative = 0;  // 1: the sync-free sweep was accepted (one host synchronisation in total)
+  int spec_flags = 0;   // why a speculative sweep was repeated on the host-driven path (spec_check_kernel bits)
   // TNB_FLAG_PROFILE: CUDA-event timings (ms) on the launching stream, per step (t = 0 is the first Gram)
   int nsteps = 0;
   double gram_ms[8] = {0}, eig_ms[8] = {0}, factor_ms[8] = {0};
@@ -289,6 +293,10 @@ struct StepCtx {
   double eps_scaled2 = 0;       // (eps / max(1, sqrt(N-1)))^2
   SweepInfo* info = nullptr;
   cudaStream_t st = 0;
+  bool exact_gram = false;      // a TF32 Gram was rejected for this tensor: take the exact-product Gram throughout
+  // speculative (sync-free) sweep
+  int* d_flags = nullptr;       // device flags raised by spec_check_kernel / cd_finish_kernel
+  int32_t* d_ranks = nullptr;   // device copy of the ranks the rule chose, [N + 1]
 };
 
 template <typename T, class ArenaT>
@@ -305,7 +313,7 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   // rule works on ratios) plus noise of ~1.6e-6 * ||G|| (measured, tests/test_model.py) — a floor under the tail
   // energies the rank rule can resolve.  An eps budget between "inactive" and 1e-4 of the trace needs finer
   // resolution than that: those sweeps take the exact-product fp64-accumulating Gram instead.
-  const bool tc_gram = cx.allow_tc && (dry || cx.eps_scaled2 < 1e-20 || cx.eps_scaled2 >= 1e-4);
+  const bool tc_gram = cx.allow_tc && !cx.exact_gram && (dry || cx.eps_scaled2 < 1e-20 || cx.eps_scaled2 >= 1e-4);
   gram_carve<T>(ar, rows, n, tc_gram, gw);
   double* G = ar.template take<double>((size_t)L * L);
   float* Gf = nullptr;
@@ -337,7 +345,18 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
   ChfsiStats cs;
   int solves = 0;
   TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, cx.sc, cx.h_sc, rm, batch_mode, &cs, &solves, st,
-                                  cx.allow_tc, concurrent));
+                                  cx.allow_tc, concurrent, used_tc));
+  if (used_tc && reinterpret_cast<const SweepScalars*>(cx.h_sc)->tf32_reject) {
+    // the spectrum is too steep for the TF32 noise floor (small_kernels.cuh::tf32_gram_rejected): same step again on
+    // the exact-product, fp64-accumulated Gram
+    if (cx.info) cx.info->tc_grams -= 1;
+    used_tc = 0;
+    TNB_TRY(gram_small_side<T>(C, rows, n, G, Gf, gw, false, nullptr, st));
+    trace_kernel<<<1, 256, 0, st>>>(G, (int)L, (int)L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
+    TNB_LAUNCH_CHECK();
+    TNB_TRY(eig_solve_and_rank<TBk>(G, reinterpret_cast<const TBk*>(Gf), L, ew, cx.sc, cx.h_sc, rm, batch_mode, &cs, &solves,
+                                    st, cx.allow_tc, concurrent, 0));
+  }
   if (cx.info) cx.info->eig_solves += solves, cx.info->chfsi_products += cs.products, cx.info->fused_filters += cs.fused_filters,
         cx.info->rr_sweeps += cs.rr_sweeps, cx.info->rr_solves += cs.outer;
   prof.mark(st);
@@ -376,14 +395,154 @@ inline int truncate_step(ArenaT& ar, bool dry, const StepCtx& cx, const T* C, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same truncation step, SPECULATIVE: enqueued without any host round trip, assuming the rank rule will return the
+// cap (rank_cap) — which it does whenever a rank cap decides (ranks_tt= with an inactive eps budget, the benchmark's
+// and the common case).  The rule still runs on the device; spec_check_kernel records what it chose and raises a flag
+// if it differs (rank-deficient data, zero unfolding), if the TF32 Gram is not accurate enough for this spectrum, or if
+// the sync-free subspace solver failed; the caller looks at the flags ONCE, after the whole sweep, and repeats the
+// decomposition on the host-driven path when any is set.  Eligibility is decided up front by spec_eligible().
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+inline bool spec_step_ok(int64_t rows, int64_t n, int64_t rank_cap, bool allow_tc) {
+  const int64_t L = rows >= n ? n : rows;
+  if (L <= JACOBI_MAX_N) return true;
+  if (!std::is_same<T, float>::value || !allow_tc) return false;
+  const int64_t k = std::min<int64_t>(rank_cap, L);
+  if (k + 16 > JACOBI_MAX_N) return false;
+  return chfsi_dev_ok((int)L, chfsi_dev_block((int)L, (int)k));
+}
+
+// The step is split in two enqueue phases so that a batch of tensors can be interleaved phase by phase (all Gram
+// kernels of a step first, then every tensor's eigen chain + projection): the whole-GPU kernels of the batch then run
+// back to back while the latency-bound eigen chains of the other tensors run beside them on their own streams.
+template <typename T>
+struct SpecStep {
+  GramWork<T> gw;
+  double *G = nullptr, *w = nullptr, *V = nullptr, *jscratch = nullptr;
+  int* jinfo = nullptr;
+  float* Gf = nullptr;
+  CdWork<float> cw;
+  T* fac = nullptr;
+  void* ptc_ws = nullptr;
+  size_t ptc_bytes = 0;
+  int ldv = 0, b = 0, used_tc = 0;
+  bool chfsi = false, tc_gram = false;
+  int64_t L = 0, kcap = 0;
+};
+
+template <typename T, class ArenaT>
+inline void spec_step_carve(ArenaT& ar, const StepCtx& cx, int64_t rows, int64_t n, int64_t rank_cap, SpecStep<T>& s) {
+  const bool tall = rows >= n;
+  s.L = tall ? n : rows;
+  const int64_t L = s.L;
+  s.tc_gram = cx.allow_tc && !cx.exact_gram;
+  gram_carve<T>(ar, rows, n, s.tc_gram, s.gw);
+  s.G = ar.template take<double>((size_t)L * L);
+  s.kcap = std::min<int64_t>(rank_cap, L);
+  s.chfsi = L > JACOBI_MAX_N;
+  s.ldv = (int)L;
+  s.b = 0;
+  s.Gf = nullptr;
+  if (!s.chfsi) {
+    s.w = ar.template take<double>(L);
+    s.V = ar.template take<double>((size_t)L * L);
+    s.jscratch = ar.template take<double>(jacobi_scratch_doubles((int)L));
+    s.jinfo = ar.template take<int>(4);
+  } else {
+    s.b = chfsi_dev_block((int)L, (int)s.kcap);
+    s.w = ar.template take<double>(s.b);
+    s.V = ar.template take<double>((size_t)L * s.b);
+    s.ldv = s.b;
+    s.Gf = ar.template take<float>((size_t)L * L);
+    chfsi_dev_carve<float>(ar, (int)L, s.b, s.cw);
+  }
+  s.fac = ar.template take<T>((size_t)L * (size_t)s.kcap);
+  s.ptc_ws = nullptr;
+  s.ptc_bytes = 0;
+  if (cx.allow_tc && std::is_same<T, float>::value && tall && rows >= PROJ_TC_MIN_ROWS && s.kcap <= PT_MAX_N && n % 4 == 0 &&
+      n >= 32) {
+    s.ptc_bytes = project_tc_workspace_bytes(n, s.kcap);
+    s.ptc_ws = ar.template take<char>(s.ptc_bytes);
+  }
+}
+
+// phase 1: Gram + trace
+template <typename T>
+inline int spec_step_gram(const StepCtx& cx, const T* C, int64_t rows, int64_t n, bool first_step, SpecStep<T>& s, bool prof_on) {
+  cudaStream_t st = cx.st;
+  Prof& prof = Prof::get();
+  if (prof_on) prof.mark(st);
+  const bool concurrent = (cx.flags & TNB_FLAG_CONCURRENT) != 0;
+  {
+    BigKernelGate gate(st, concurrent && s.gw.tc_ws != nullptr);
+    TNB_TRY(gram_small_side<T>(C, rows, n, s.G, s.Gf, s.gw, s.tc_gram, &s.used_tc, st));
+  }
+  if (cx.info) cx.info->tc_grams += s.used_tc;
+  trace_kernel<<<1, 256, 0, st>>>(s.G, (int)s.L, (int)s.L, cx.sc, first_step ? 1 : 0, cx.eps_scaled2);
+  TNB_LAUNCH_CHECK();
+  if (prof_on) prof.mark(st);
+  return TNB_OK;
+}
+
+// phase 2: eigenpairs, rank rule + speculation check, factor extraction, projection
+template <typename T>
+inline int spec_step_rest(const StepCtx& cx, const T* C, int64_t rows, int64_t n, int32_t rm, T* core, T* Cn, int mu,
+                          SpecStep<T>& s, bool prof_on) {
+  const bool tall = rows >= n;
+  const int64_t L = s.L;
+  const int batch_mode = (cx.flags & TNB_FLAG_BATCH_MODE) ? 1 : 0;
+  cudaStream_t st = cx.st;
+  Prof& prof = Prof::get();
+  const bool concurrent = (cx.flags & TNB_FLAG_CONCURRENT) != 0;
+  if (!s.chfsi) {
+    // a TF32 Gram is accurate to ~2e-6 ||G||: rotating it in fp32 (backward error ~1e-6 ||G||, covered by the accept rule's
+    // noise allowance) is consistent with it and 3-4x cheaper than fp64 on this machine (~16 fp64 FMAs / clk / SM);
+    // eigenvalues still come out as fp64 Rayleigh quotients and the vectors are re-orthonormalised (jacobi2.cuh)
+    const bool single = s.used_tc != 0 && jacobi2_ok((int)L, true);
+    TNB_TRY(jacobi2_eigh(s.G, (int)L, (int)L, s.w, s.V, s.jscratch, s.jinfo, st, single, single ? 2e-6 : 0.0));
+    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)L, rm, 0, batch_mode, cx.sc, s.used_tc, (int)L);
+  } else {
+    TNB_TRY(eig_topk_chfsi_dev(s.Gf, (int)L, (int)s.kcap, s.b, &cx.sc->trace, 1e-6, s.cw, s.w, s.V, cx.d_flags, st));
+    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)s.kcap, rm, 1, batch_mode, cx.sc, s.used_tc, s.b);
+    if (cx.info) cx.info->eig_solves += 1;
+  }
+  TNB_LAUNCH_CHECK();
+  spec_check_kernel<<<1, 32, 0, st>>>(cx.sc, (int)s.kcap, cx.d_ranks + mu, cx.d_flags);
+  TNB_LAUNCH_CHECK();
+  if (prof_on) prof.mark(st);
+  const int64_t rank = s.kcap;
+  if (tall) {
+    scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(s.V, s.ldv, (int)n, (int)rank, s.w, core, 0, 1);
+    TNB_LAUNCH_CHECK();
+    scale_extract_kernel<T><<<grid_for(n * rank), 256, 0, st>>>(s.V, s.ldv, (int)n, (int)rank, s.w, s.fac, 0, 0);
+    TNB_LAUNCH_CHECK();
+    {
+      BigKernelGate gate(st, concurrent && rows >= PROJ_TC_MIN_ROWS);
+      TNB_TRY(project_any<T>(C, rows, n, s.fac, rank, Cn, st, s.ptc_ws, s.ptc_bytes));
+    }
+  } else {
+    scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(s.V, s.ldv, (int)rows, (int)rank, s.w, s.fac, 1, 0);
+    TNB_LAUNCH_CHECK();
+    TNB_TRY((gemm_direct<T, T, T, T>(rank, n, rows, s.fac, rank, false, C, n, false, core, n, (T)1, nullptr, 0, (T)0,
+                                     nullptr, 0, (T)0, st)));
+    scale_extract_kernel<T><<<grid_for(rows * rank), 256, 0, st>>>(s.V, s.ldv, (int)rows, (int)rank, s.w, Cn, 2, 0);
+    TNB_LAUNCH_CHECK();
+  }
+  if (prof_on) prof.mark(st);
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dense TT-SVD
 // ---------------------------------------------------------------------------------------------
 template <typename T, class ArenaT>
-inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, const int32_t* rmax, double eps,
-                      uint32_t flags, T* cores, int32_t* ranks_host, SweepInfo* info, cudaStream_t st) {
+inline int ttsvd_sync_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, const int32_t* rmax, double eps,
+                           uint32_t flags, T* cores, int32_t* ranks_host, SweepInfo* info, cudaStream_t st,
+                           bool exact_gram = false) {
   const int N = d.N;
   StepCtx cx;
   cx.flags = flags;
+  cx.exact_gram = exact_gram;
   cx.allow_tc = !(flags & TNB_FLAG_NO_TENSORCORE) && (dry || tc_path_available());
   cx.info = info;
   cx.st = st;
@@ -452,6 +611,320 @@ inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, c
       }
     }
     prof.on = false;
+  }
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Speculative dense TT-SVD: the whole right-to-left sweep enqueued in one go, ONE synchronisation at the end.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+inline bool spec_eligible(const SweepDims& d, const int32_t* rmax, double eps, uint32_t flags, bool allow_tc) {
+  static const bool disabled = getenv("TNB_NO_SPECULATE") != nullptr;  // A/B switch (profiling, debugging)
+  if (disabled || (flags & TNB_FLAG_NO_SPECULATE) || d.N < 2 || !rmax) return false;
+  const double epsN = eps / std::max(1.0, std::sqrt((double)(d.N - 1)));
+  if (!(epsN * epsN < 1e-20)) return false;  // an active eps budget decides ranks: host-driven path
+  for (int mu = d.N - 1; mu >= 1; --mu) {
+    if (rmax[mu - 1] <= 0) return false;
+    if (!spec_step_ok<T>(d.rows[mu], d.shape[mu] * d.rcap[mu + 1], d.rcap[mu], allow_tc)) return false;
+  }
+  return true;
+}
+
+struct SpecOutcome {
+  int flags = 0;
+  bool ran = false;
+};
+
+struct SpecHostBack {  // pinned read-back of one speculative sweep
+  SweepScalars sc;
+  int flags[4];
+  int32_t ranks[64];
+};
+
+// One tensor of a speculative sweep (or of a batch of them): its arena, device scalars, carries and position.
+template <typename T, class ArenaT>
+struct SpecRun {
+  ArenaT* ar = nullptr;
+  StepCtx cx;
+  SweepInfo info_local;
+  const T* C = nullptr;
+  T* carry[2] = {nullptr, nullptr};
+  T* cores = nullptr;
+  SpecStep<T> step;
+  size_t mark = 0, peak = 0;
+  SpecHostBack* hb = nullptr;
+};
+
+template <typename T, class ArenaT>
+inline int spec_begin(SpecRun<T, ArenaT>& r, ArenaT& ar, bool dry, const T* data, const SweepDims& d, double eps,
+                      uint32_t flags, T* cores, SweepInfo* info, cudaStream_t st, SpecHostBack* hb) {
+  const int N = d.N;
+  r.ar = &ar;
+  r.cx = StepCtx();
+  r.cx.flags = flags;
+  r.cx.allow_tc = !(flags & TNB_FLAG_NO_TENSORCORE) && (dry || tc_path_available());
+  r.cx.info = info;
+  r.cx.st = st;
+  const double epsN = eps / std::max(1.0, std::sqrt((double)(N - 1)));
+  r.cx.eps_scaled2 = epsN * epsN;
+  r.cx.sc = ar.template take<SweepScalars>(1);
+  r.cx.d_flags = ar.template take<int>(4);
+  r.cx.d_ranks = ar.template take<int32_t>(N + 1);
+  size_t carry_elems[2] = {0, 0};
+  for (int mu = N - 1, t = 0; mu >= 1; --mu, ++t) {
+    const size_t e = (size_t)d.rows[mu] * (size_t)d.rcap[mu];
+    if (e > carry_elems[t & 1]) carry_elems[t & 1] = e;
+  }
+  r.carry[0] = ar.template take<T>(carry_elems[0]);
+  r.carry[1] = ar.template take<T>(carry_elems[1]);
+  r.C = data;
+  r.cores = cores;
+  r.peak = ar.off;
+  r.hb = hb;
+  if (!dry) TNB_CUDA(cudaMemsetAsync(r.cx.d_flags, 0, 4 * sizeof(int), st));
+  return TNB_OK;
+}
+
+// the step scratch of step t+1 reuses that of step t: the kernels of one stream run in order, and every kernel of
+// step t+1 that writes scratch is enqueued after every kernel of step t that reads it
+template <typename T, class ArenaT>
+inline int spec_phase1(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, int mu, int t, bool prof_on) {
+  ArenaT& ar = *r.ar;
+  r.mark = ar.off;
+  spec_step_carve<T>(ar, r.cx, d.rows[mu], d.shape[mu] * d.rcap[mu + 1], d.rcap[mu], r.step);
+  if (ar.off > r.peak) r.peak = ar.off;
+  if (dry) return TNB_OK;
+  if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "workspace too small (need > %zu bytes)", ar.off);
+  return spec_step_gram<T>(r.cx, r.C, d.rows[mu], d.shape[mu] * d.rcap[mu + 1], t == 0, r.step, prof_on);
+}
+template <typename T, class ArenaT>
+inline int spec_phase2(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, const int32_t* rmax, int mu, int t, bool prof_on) {
+  ArenaT& ar = *r.ar;
+  if (!dry) {
+    TNB_TRY(spec_step_rest<T>(r.cx, r.C, d.rows[mu], d.shape[mu] * d.rcap[mu + 1], rmax[mu - 1], r.cores + d.slot[mu],
+                              r.carry[t & 1], mu, r.step, prof_on));
+    r.C = r.carry[t & 1];
+  }
+  ar.off = r.mark;
+  return TNB_OK;
+}
+template <typename T, class ArenaT>
+inline int spec_end(SpecRun<T, ArenaT>& r, const SweepDims& d) {
+  cudaStream_t st = r.cx.st;
+  const int N = d.N;
+  TNB_CUDA(cudaMemcpyAsync(r.cores + d.slot[0], r.C, sizeof(T) * (size_t)d.shape[0] * (size_t)d.rcap[1],
+                           cudaMemcpyDeviceToDevice, st));
+  TNB_CUDA(cudaMemcpyAsync(&r.hb->sc, r.cx.sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(cudaMemcpyAsync(r.hb->flags, r.cx.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(cudaMemcpyAsync(r.hb->ranks, r.cx.d_ranks, (size_t)(N + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return TNB_OK;
+}
+// after the stream has been synchronised
+inline void spec_collect(const SpecHostBack* hb, const SweepDims& d, int32_t* ranks_host, SweepInfo* info, SpecOutcome* out) {
+  const int N = d.N;
+  out->ran = true;
+  out->flags = hb->flags[0];
+  ranks_host[0] = 1;
+  ranks_host[N] = 1;
+  for (int mu = 1; mu < N; ++mu) ranks_host[mu] = (int32_t)d.rcap[mu];  // the flags say whether the rule agreed
+  if (info) {
+    info->norm = std::sqrt(hb->sc.norm2 > 0 ? hb->sc.norm2 : 0.0);
+    info->chfsi_products += hb->flags[1];
+    info->rr_solves += hb->flags[2];
+    info->rr_sweeps += hb->flags[3];
+    info->fused_filters += hb->flags[2] - info->eig_solves;  // every Rayleigh-Ritz step but the first of a solve follows a filter
+  }
+}
+
+template <typename T, class ArenaT>
+inline int ttsvd_spec_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, const int32_t* rmax, double eps,
+                           uint32_t flags, T* cores, int32_t* ranks_host, SweepInfo* info, cudaStream_t st,
+                           SpecOutcome* out) {
+  const int N = d.N;
+  Prof& prof = Prof::get();
+  prof.on = !dry && (flags & TNB_FLAG_PROFILE);
+  prof.used = 0;
+  const bool prof_on = prof.on;
+  SpecHostBack* hb = nullptr;
+  if (!dry) {
+    hb = static_cast<SpecHostBack*>(pinned_scratch(sizeof(SpecHostBack)));
+    if (!hb) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
+  }
+  SpecRun<T, ArenaT> r;
+  TNB_TRY((spec_begin<T, ArenaT>(r, ar, dry, data, d, eps, flags, cores, info, st, hb)));
+  for (int mu = N - 1, t = 0; mu >= 1; --mu, ++t) {
+    int rc = spec_phase1<T, ArenaT>(r, dry, d, mu, t, prof_on);
+    if (rc == TNB_OK) rc = spec_phase2<T, ArenaT>(r, dry, d, rmax, mu, t, prof_on);
+    if (rc != TNB_OK) {
+      if (!dry) cudaStreamSynchronize(st);  // part of the sweep is enqueued: drain it before the host-driven path
+      prof.on = false;
+      return rc;
+    }
+  }
+  if (dry) {
+    ar.off = r.peak;
+    return TNB_OK;
+  }
+  TNB_TRY((spec_end<T, ArenaT>(r, d)));
+  TNB_CUDA(cudaStreamSynchronize(st));
+  spec_collect(hb, d, ranks_host, info, out);
+  if (prof_on && info) {
+    const int steps = prof.used / 4;
+    info->nsteps = steps;
+    for (int t = 0; t < steps && t < 8; ++t) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, prof.ev[4 * t], prof.ev[4 * t + 1]);
+      cudaEventElapsedTime(&b, prof.ev[4 * t + 1], prof.ev[4 * t + 2]);
+      cudaEventElapsedTime(&c, prof.ev[4 * t + 2], prof.ev[4 * t + 3]);
+      info->gram_ms[t] = a;
+      info->eig_ms[t] = b;
+      info->factor_ms[t] = c;
+    }
+  }
+  prof.on = false;
+  return TNB_OK;
+}
+
+// Dispatcher: speculative sweep when a rank cap decides every bond, host-driven sweep otherwise and as the fallback.
+template <typename T, class ArenaT>
+inline int ttsvd_impl(ArenaT& ar, bool dry, const T* data, const SweepDims& d, const int32_t* rmax, double eps,
+                      uint32_t flags, T* cores, int32_t* ranks_host, SweepInfo* info, cudaStream_t st) {
+  const bool allow_tc = !(flags & TNB_FLAG_NO_TENSORCORE) && (dry || tc_path_available());
+  // the sizing pass cannot ask the device what it supports: size for both paths
+  const bool spec = dry ? (d.N >= 2 && rmax != nullptr) : spec_eligible<T>(d, rmax, eps, flags, allow_tc);
+  const size_t base = ar.off;
+  size_t need_spec = 0;
+  if (spec) {
+    if (dry) {
+      bool all_caps = true;
+      for (int mu = 1; mu < d.N; ++mu) all_caps = all_caps && rmax[mu - 1] > 0;
+      if (all_caps) {
+        SpecOutcome o;
+        const int rc = ttsvd_spec_impl<T>(ar, true, data, d, rmax, eps, flags, cores, ranks_host, info, st, &o);
+        if (rc == TNB_OK) need_spec = ar.off - base;
+        ar.off = base;
+      }
+    } else {
+      SpecOutcome o;
+      SweepInfo saved;
+      if (info) saved = *info;
+      const int rc = ttsvd_spec_impl<T>(ar, false, data, d, rmax, eps, flags, cores, ranks_host, info, st, &o);
+      if (rc == TNB_OK && o.ran && o.flags == 0) {
+        if (info) info->speculative = 1;
+        return TNB_OK;
+      }
+      if (rc != TNB_OK && rc != TNB_ERR_UNSUPPORTED && rc != TNB_ERR_NOCONV) return rc;
+      // the device disagreed with the speculation (or could not run the sync-free solver): host-driven sweep;
+      // bit 0 = the TF32 Gram is too coarse for this spectrum, so the repeat takes exact-product Gram matrices
+      if (info) { *info = saved; info->spec_flags = o.flags; }
+      ar.off = base;
+      ar.ok = true;
+      return ttsvd_sync_impl<T>(ar, false, data, d, rmax, eps, flags, cores, ranks_host, info, st, (o.flags & 1) != 0);
+    }
+  }
+  const int rc = ttsvd_sync_impl<T>(ar, dry, data, d, rmax, eps, flags, cores, ranks_host, info, st);
+  if (dry && rc == TNB_OK && need_spec > ar.off - base) ar.off = base + need_spec;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A batch of independent dense tensors of one shape (the reference's `batch=True` constructor, tensor.py:401-408 with
+// a leading batch dimension; north_star: "batched decompositions").  Up to `inflight` speculative sweeps are enqueued
+// from ONE host thread, interleaved phase by phase on internal streams, and synchronised once; tensors whose
+// speculation the device rejected are then repeated one by one on the host-driven path.
+// ---------------------------------------------------------------------------------------------
+constexpr int TNB_BATCH_MAX_INFLIGHT = 8;
+
+struct StreamPool {
+  cudaStream_t st[TNB_BATCH_MAX_INFLIGHT] = {};
+  cudaEvent_t ev[TNB_BATCH_MAX_INFLIGHT + 1] = {};
+  bool ready = false;
+  std::mutex mu;
+  int ensure() {
+    if (ready) return TNB_OK;
+    for (int i = 0; i < TNB_BATCH_MAX_INFLIGHT; ++i) TNB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    for (int i = 0; i <= TNB_BATCH_MAX_INFLIGHT; ++i) TNB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    ready = true;
+    return TNB_OK;
+  }
+  static StreamPool& get() {
+    static StreamPool pools[TNB_MAX_DEVICES];
+    return pools[current_device_index()];
+  }
+};
+
+template <typename T>
+inline int ttsvd_batch_impl(void* workspace, size_t per_tensor_bytes, int inflight, const T* const* data, int batch,
+                            const SweepDims& d, const int32_t* rmax, double eps, uint32_t flags, T* const* cores,
+                            int32_t* ranks_host, double* norms_host, int32_t* spec_host, cudaStream_t st) {
+  const int N = d.N;
+  const bool allow_tc = !(flags & TNB_FLAG_NO_TENSORCORE) && tc_path_available();
+  const bool spec = batch > 0 && spec_eligible<T>(d, rmax, eps, flags, allow_tc);
+  char* ws = static_cast<char*>(workspace);
+  if (!spec || inflight < 2 || batch < 2) {  // one at a time through the dispatcher (speculative when eligible)
+    for (int i = 0; i < batch; ++i) {
+      Arena ar(ws, per_tensor_bytes);
+      SweepInfo info;
+      TNB_TRY((ttsvd_impl<T, Arena>(ar, false, data[i], d, rmax, eps, flags, cores[i], ranks_host + (size_t)i * (N + 1), &info, st)));
+      if (norms_host) norms_host[i] = info.norm;
+      if (spec_host) spec_host[i] = info.speculative;
+    }
+    return TNB_OK;
+  }
+  if (inflight > TNB_BATCH_MAX_INFLIGHT) inflight = TNB_BATCH_MAX_INFLIGHT;
+  if (inflight > batch) inflight = batch;
+  StreamPool& pool = StreamPool::get();
+  std::lock_guard<std::mutex> lk(pool.mu);  // one batch at a time per device uses the internal streams
+  TNB_TRY(pool.ensure());
+  SpecHostBack* hbs = static_cast<SpecHostBack*>(pinned_scratch((size_t)batch * sizeof(SpecHostBack)));
+  if (!hbs) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
+  // fork: the internal streams start after whatever the caller enqueued on `st`
+  TNB_CUDA(cudaEventRecord(pool.ev[TNB_BATCH_MAX_INFLIGHT], st));
+  for (int s = 0; s < inflight; ++s) TNB_CUDA(cudaStreamWaitEvent(pool.st[s], pool.ev[TNB_BATCH_MAX_INFLIGHT], 0));
+  const uint32_t bflags = (flags | TNB_FLAG_CONCURRENT) & ~TNB_FLAG_PROFILE;
+  std::vector<SweepInfo> infos(batch);
+  int rc = TNB_OK;
+  for (int g0 = 0; g0 < batch && rc == TNB_OK; g0 += inflight) {
+    const int g = std::min(inflight, batch - g0);
+    std::vector<Arena> arenas;
+    arenas.reserve(g);
+    std::vector<SpecRun<T, Arena>> runs(g);
+    for (int s = 0; s < g; ++s) arenas.emplace_back(ws + (size_t)s * per_tensor_bytes, per_tensor_bytes);
+    for (int s = 0; s < g && rc == TNB_OK; ++s)
+      rc = spec_begin<T, Arena>(runs[s], arenas[s], false, data[g0 + s], d, eps, bflags, cores[g0 + s], &infos[g0 + s],
+                                pool.st[s], hbs + g0 + s);
+    for (int mu = N - 1, t = 0; mu >= 1 && rc == TNB_OK; --mu, ++t) {
+      for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase1<T, Arena>(runs[s], false, d, mu, t, false);
+      for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, mu, t, false);
+    }
+    for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_end<T, Arena>(runs[s], d);
+  }
+  // join: the caller's stream continues after every internal stream; then the one host synchronisation
+  for (int s = 0; s < inflight; ++s) {
+    cudaEventRecord(pool.ev[s], pool.st[s]);
+    cudaStreamWaitEvent(st, pool.ev[s], 0);
+  }
+  TNB_CUDA(cudaStreamSynchronize(st));
+  if (rc != TNB_OK && rc != TNB_ERR_UNSUPPORTED && rc != TNB_ERR_NOCONV) return rc;
+  // read every outcome out of the pinned block first: the host-driven repeats below reuse that scratch
+  std::vector<SpecOutcome> outs(batch);
+  for (int i = 0; i < batch; ++i)
+    if (rc == TNB_OK) spec_collect(hbs + i, d, ranks_host + (size_t)i * (N + 1), &infos[i], &outs[i]);
+  for (int i = 0; i < batch; ++i) {
+    int32_t* rk = ranks_host + (size_t)i * (N + 1);
+    if (rc == TNB_OK && outs[i].flags == 0) {
+      if (norms_host) norms_host[i] = infos[i].norm;
+      if (spec_host) spec_host[i] = 1;
+      continue;
+    }
+    // repeat this tensor on the host-driven path (exact Gram when the TF32 one was rejected)
+    Arena ar(ws, per_tensor_bytes);
+    SweepInfo info;
+    TNB_TRY((ttsvd_sync_impl<T, Arena>(ar, false, data[i], d, rmax, eps, flags & ~TNB_FLAG_PROFILE, cores[i], rk, &info, st,
+                                       (outs[i].flags & 1) != 0)));
+    if (norms_host) norms_host[i] = info.norm;
+    if (spec_host) spec_host[i] = 0;
   }
   return TNB_OK;
 }

@@ -96,7 +96,9 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
     info_host[31] = info.fused_filters;
     info_host[29] = info.rr_sweeps;
     info_host[30] = info.rr_solves;
-    for (int t = 0; t < info.nsteps && t < 7; ++t) {
+    info_host[26] = info.speculative;
+    info_host[27] = info.spec_flags;
+    for (int t = 0; t < info.nsteps && t < 6; ++t) {
       info_host[4] += info.gram_ms[t];
       info_host[5] += info.eig_ms[t];
       info_host[6] += info.factor_ms[t];
@@ -106,6 +108,46 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
     }
   }
   return rc;
+}
+
+size_t tnb_ttsvd_batch_workspace_bytes(int dtype, int batch, int ndim, const int64_t* shape, const int32_t* rmax,
+                                       uint32_t flags, size_t* per_tensor_bytes) {
+  const size_t one = tnb_ttsvd_workspace_bytes(dtype, ndim, shape, rmax, flags);
+  if (per_tensor_bytes) *per_tensor_bytes = one;
+  if (one == 0 || batch < 1) return 0;
+  const int inflight = batch < 6 ? batch : 6;  // measured on B200: the eigen chains of 6 tensors cover the big kernels
+  return one * (size_t)inflight;
+}
+
+int tnb_ttsvd_batch(int dtype, const void* const* data, int batch, int ndim, const int64_t* shape, const int32_t* rmax,
+                    double eps, uint32_t flags, void* workspace, size_t workspace_bytes, void* const* cores,
+                    int64_t cores_capacity, int32_t* ranks_host, double* norms_host, int32_t* speculative_host,
+                    void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (batch < 0 || (batch > 0 && (!data || !cores)) || !shape || !ranks_host || !workspace)
+    return fail(TNB_ERR_INVALID, "tnb_ttsvd_batch: null argument");
+  if (rmax)
+    for (int k = 0; k < ndim - 1; ++k)
+      if (rmax[k] < 0) return fail(TNB_ERR_INVALID, "rmax[%d] must be >= 1 (or 0 for none)", k);
+  SweepDims d;
+  TNB_TRY(make_dims(ndim, shape, rmax, d));
+  if (cores_capacity < d.capacity)
+    return fail(TNB_ERR_WORKSPACE, "tnb_ttsvd_batch: cores buffers hold %lld elements, need %lld", (long long)cores_capacity,
+                (long long)d.capacity);
+  for (int i = 0; i < batch; ++i)
+    if (!data[i] || !cores[i]) return fail(TNB_ERR_INVALID, "tnb_ttsvd_batch: null tensor %d", i);
+  const size_t one = tnb_ttsvd_workspace_bytes(dtype, ndim, shape, rmax, flags);
+  if (one == 0) return fail(TNB_ERR_UNSUPPORTED, "tnb_ttsvd_batch: unsupported shape");
+  if (workspace_bytes < one) return fail(TNB_ERR_WORKSPACE, "tnb_ttsvd_batch: workspace %zu < %zu", workspace_bytes, one);
+  const int inflight = (int)std::min<size_t>(workspace_bytes / one, (size_t)TNB_BATCH_MAX_INFLIGHT);
+  if (dtype == TNB_F32)
+    return ttsvd_batch_impl<float>(workspace, one, inflight, reinterpret_cast<const float* const*>(data), batch, d, rmax, eps,
+                                   flags, reinterpret_cast<float* const*>(cores), ranks_host, norms_host, speculative_host,
+                                   as_stream(stream));
+  return ttsvd_batch_impl<double>(workspace, one, inflight, reinterpret_cast<const double* const*>(data), batch, d, rmax, eps,
+                                  flags, reinterpret_cast<double* const*>(cores), ranks_host, norms_host, speculative_host,
+                                  as_stream(stream));
 }
 
 int tnb_ttsvd_host(int dtype, const void* data_host, int ndim, const int64_t* shape, const int32_t* rmax, double eps,

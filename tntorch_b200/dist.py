@@ -78,7 +78,8 @@ def ttsvd_batch_sharded(tensors: Sequence[torch.Tensor], rmax=None, eps: float =
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     lo, hi = shard_range(len(tensors), world, rank)
-    local = [ops.ttsvd(tensors[i], rmax=rmax, eps=eps) for i in range(lo, hi)]
+    # the local shard goes through ONE library call (tnb_ttsvd_batch: several tensors in flight per GPU)
+    local = ops.ttsvd_batch([tensors[i] for i in range(lo, hi)], rmax=rmax, eps=eps) if hi > lo else []
     return all_gather_cores(local, len(tensors)) if gather else local
 
 

@@ -70,7 +70,7 @@ def has_tensorcore_path() -> bool:
 
 # --------------------------------------------------------------------------------------
 def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = False, use_tensorcore: bool = True,
-          return_info: bool = False, concurrent: bool = False):
+          return_info: bool = False, concurrent: bool = False, speculate: bool = True):
     """Dense tensor -> list of TT cores [r_{k-1}, I_k, r_k] (tn.Tensor(data, ranks_tt=...), tensor.py:401-408)."""
     _require_cuda(data, "ttsvd")
     data = data.contiguous()
@@ -79,7 +79,7 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
     shape = list(data.shape)
     rm = _rmax_list(rmax, max(N - 1, 0))
     flags = ((0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_BATCH_MODE if batch_mode else 0) |
-             (_lib.FLAG_CONCURRENT if concurrent else 0))
+             (_lib.FLAG_CONCURRENT if concurrent else 0) | (0 if speculate else _lib.FLAG_NO_SPECULATE))
     L = lib()
     sh = i64(shape)
     rmc = i32(rm) if N > 1 else i32([0])
@@ -103,7 +103,8 @@ def ttsvd(data: torch.Tensor, rmax=None, eps: float = 1e-14, batch_mode: bool = 
         cores.append(cores_buf[offs[k]: offs[k] + r0 * shape[k] * r1].view(r0, shape[k], r1))
     if return_info:
         return cores, dict(norm=info[0], eig_solves=int(info[1]), chfsi_products=int(info[2]), tc_grams=int(info[3]),
-                           fused_filters=int(info[31]), rr_sweeps=int(info[29]), outer_iterations=int(info[30]))
+                           fused_filters=int(info[31]), rr_sweeps=int(info[29]), outer_iterations=int(info[30]),
+                           speculative=int(info[26]), spec_flags=int(info[27]))
     return cores
 
 
@@ -111,7 +112,7 @@ class TTSVDPlan:
     """Pre-allocated buffers for repeated decompositions of one shape (bench.py, serving loops)."""
 
     def __init__(self, shape: Sequence[int], dtype: torch.dtype, rmax=None, device="cuda", use_tensorcore: bool = True,
-                 host_io: bool = False, profile: bool = False, concurrent: bool = False):
+                 host_io: bool = False, profile: bool = False, concurrent: bool = False, speculate: bool = True):
         self.shape = [int(s) for s in shape]
         self.N = len(self.shape)
         self.dtype = dtype
@@ -120,7 +121,7 @@ class TTSVDPlan:
         self.rm = _rmax_list(rmax, max(self.N - 1, 0))
         # concurrent: several plans run at once on different streams (TNB_FLAG_CONCURRENT, include/tnb200.h)
         self.flags = ((0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_PROFILE if profile else 0) |
-                      (_lib.FLAG_CONCURRENT if concurrent else 0))
+                      (_lib.FLAG_CONCURRENT if concurrent else 0) | (0 if speculate else _lib.FLAG_NO_SPECULATE))
         L = lib()
         self._sh = i64(self.shape)
         self._rm = i32(self.rm) if self.N > 1 else i32([0])
@@ -164,6 +165,104 @@ class TTSVDPlan:
             r0, r1 = self.ranks[k], self.ranks[k + 1]
             out.append(buf[self._offs[k]: self._offs[k] + r0 * self.shape[k] * r1].view(r0, self.shape[k], r1))
         return out
+
+
+class TTSVDBatchPlan:
+    """Pre-allocated buffers for decomposing batches of `batch` dense tensors of one shape through tnb_ttsvd_batch
+    (tn.Tensor(X[B, ...], ranks_tt=r, batch=True); bench.py; dist.ttsvd_batch_sharded).  Up to `inflight` tensors are
+    in flight at once inside the library (internal streams, one enqueueing thread, one synchronisation)."""
+
+    def __init__(self, shape: Sequence[int], dtype: torch.dtype, batch: int, rmax=None, device="cuda", inflight: int = 6,
+                 use_tensorcore: bool = True, batch_mode: bool = False, host_io: bool = False):
+        self.shape = [int(s) for s in shape]
+        self.N = len(self.shape)
+        self.batch = int(batch)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.code = _DT[dtype]
+        self.rm = _rmax_list(rmax, max(self.N - 1, 0))
+        self.flags = (0 if use_tensorcore else _lib.FLAG_NO_TENSORCORE) | (_lib.FLAG_BATCH_MODE if batch_mode else 0)
+        L = lib()
+        self._sh = i64(self.shape)
+        self._rm = i32(self.rm) if self.N > 1 else i32([0])
+        self._offs = (C.c_int64 * self.N)()
+        self.cap = L.tnb_ttsvd_cores_capacity(self.N, self._sh, self._rm, self._offs)
+        one = C.c_size_t(0)
+        L.tnb_ttsvd_batch_workspace_bytes(self.code, self.batch, self.N, self._sh, self._rm, self.flags, C.byref(one))
+        if self.cap < 0 or one.value == 0:
+            check(_lib.ERR_UNSUPPORTED)
+        self.per_tensor_bytes = int(one.value)
+        self.inflight = max(1, min(int(inflight), self.batch, 8))
+        self.ws = _ws(self.per_tensor_bytes * self.inflight, self.device)
+        self.cores_buf = torch.empty(self.batch, int(self.cap), dtype=dtype, device=self.device)
+        self.ranks = (C.c_int32 * (self.batch * (self.N + 1)))()
+        self.norms = (C.c_double * self.batch)()
+        self.spec = (C.c_int32 * self.batch)()
+        self.numel = 1
+        for s in self.shape:
+            self.numel *= s
+        self._cores_ptrs = (C.c_void_p * self.batch)(*[self.cores_buf[i].data_ptr() for i in range(self.batch)])
+        self.dev_in = None
+        self.cores_host = None
+        if host_io:
+            self.dev_in = torch.empty(self.batch, self.numel, dtype=dtype, device=self.device)
+            self.cores_host = torch.empty(self.batch, int(self.cap), dtype=dtype, pin_memory=True)
+
+    def run(self, tensors, eps: float = 1e-14):
+        """tensors: a [batch, ...] tensor or a sequence of `batch` contiguous device tensors.  Returns, per tensor, the
+        list of its cores (views of the plan's buffers: valid until the next run)."""
+        if isinstance(tensors, torch.Tensor):
+            tensors = [tensors[i] for i in range(tensors.shape[0])]
+        assert len(tensors) == self.batch
+        keep = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+        ptrs = (C.c_void_p * self.batch)(*[t.data_ptr() for t in keep])
+        with torch.cuda.device(self.device):
+            check(lib().tnb_ttsvd_batch(self.code, ptrs, self.batch, self.N, self._sh, self._rm, float(eps), self.flags,
+                                        _ptr(self.ws), self.ws.numel(), self._cores_ptrs, self.cap, self.ranks, self.norms,
+                                        self.spec, _stream()))
+        return [self._views(self.cores_buf[i], i) for i in range(self.batch)]
+
+    def run_host(self, tensors_host: torch.Tensor, eps: float = 1e-14):
+        """End to end on HOST buffers: `tensors_host` [batch, ...] in (pinned) host memory -> device, decomposition,
+        cores back to pinned host memory.  The copy of tensor i+1 overlaps nothing here (one stream): the PCIe link is
+        the bound either way."""
+        assert self.dev_in is not None, "construct the plan with host_io=True"
+        flat = tensors_host.reshape(self.batch, self.numel)
+        self.dev_in.copy_(flat, non_blocking=True)
+        self.run(self.dev_in.view([self.batch] + self.shape), eps)
+        self.cores_host.copy_(self.cores_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [self._views(self.cores_host[i], i) for i in range(self.batch)]
+
+    def _views(self, buf, i):
+        out = []
+        base = i * (self.N + 1)
+        for k in range(self.N):
+            r0, r1 = self.ranks[base + k], self.ranks[base + k + 1]
+            out.append(buf[self._offs[k]: self._offs[k] + r0 * self.shape[k] * r1].view(r0, self.shape[k], r1))
+        return out
+
+
+def ttsvd_batch(tensors, rmax=None, eps: float = 1e-14, batch_mode: bool = False, inflight: int = 6,
+                use_tensorcore: bool = True, return_info: bool = False):
+    """Decompose a batch of dense tensors of one shape (a [B, ...] tensor or a sequence): tn.Tensor(..., batch=True)
+    and every caller that decomposes many tensors.  Returns a list (per tensor) of lists of cores (fresh tensors)."""
+    if isinstance(tensors, torch.Tensor):
+        tensors = [tensors[i] for i in range(tensors.shape[0])]
+    if len(tensors) == 0:
+        return ([], dict(speculative=[])) if return_info else []
+    t0 = tensors[0]
+    _require_cuda(t0, "ttsvd_batch")
+    for t in tensors:
+        if t.shape != t0.shape or t.dtype != t0.dtype or t.device != t0.device:
+            raise ValueError("ttsvd_batch: all tensors must share shape, dtype and device")
+    plan = TTSVDBatchPlan(t0.shape, t0.dtype, len(tensors), rmax=rmax, device=t0.device, inflight=inflight,
+                          use_tensorcore=use_tensorcore, batch_mode=batch_mode)
+    views = plan.run(tensors, eps)
+    out = [[c.clone() for c in cores] for cores in views]
+    if return_info:
+        return out, dict(speculative=[int(x) for x in plan.spec], norms=[float(x) for x in plan.norms])
+    return out
 
 
 # --------------------------------------------------------------------------------------

@@ -114,7 +114,8 @@ class Tensor(object):
                 Us = self.Us
             elif batch:
                 # the reference's batch mode: per-sample decomposition, rank = min(rmax, len(S)), no eps
-                per = [ops.ttsvd(data[b], rmax=ranks_tt, batch_mode=True) for b in range(data.shape[0])]
+                # one library call for the whole batch: several samples in flight inside libtnb200 (tnb_ttsvd_batch)
+                per = ops.ttsvd_batch(data, rmax=ranks_tt, batch_mode=True)
                 self.cores = [torch.stack([p[k] for p in per], dim=0) for k in range(N)]
             else:
                 self.cores = ops.ttsvd(data, rmax=ranks_tt)
