@@ -134,6 +134,37 @@ int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t
                  void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Linear combinations of TT tensors, optionally fused with the rounding that follows them.
+ * Replaces: Tensor.__add__ / __sub__ / scalar * for TT operands (tensor.py:445-520: block cores — first core side by
+ *           side, interior cores block diagonal, last core stacked) and the `tn.round(function(a, b))` step of
+ *           tools.reduce (tools.py:460-512), metrics.hadamard_sum (metrics.py:384-446) and every caller that adds and
+ *           re-rounds in a loop.
+ *   cores_in   noperands * ndim device pointers, operand-major (cores_in[k * ndim + n] = core n of operand k, shape
+ *              [r_n, I_n, r_{n+1}]); ranks_in: noperands * (ndim + 1) ints; alpha: noperands doubles (NULL = all 1),
+ *              applied to the first core like the reference's `t * scalar`; at most 16 operands per call
+ *   tnb_tt_sum        writes the block cores (summed ranks through tnb_tt_sum_cores_capacity)
+ *   tnb_tt_sum_round  assembles them in the workspace and runs the tnb_tt_round sweeps on them in the same call: no
+ *                     intermediate tensor exists on the host side; output layout as tnb_tt_round
+ * ------------------------------------------------------------------------------------------ */
+int64_t tnb_tt_sum_cores_capacity(int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                  int32_t* ranks_sum_host, int64_t* core_offsets_host);
+int tnb_tt_sum(int dtype, const void* const* cores_in, int noperands, const double* alpha, int ndim, const int64_t* shape,
+               const int32_t* ranks_in, void* cores_out, int64_t cores_capacity, void* stream);
+int64_t tnb_tt_sum_round_cores_capacity(int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                        const int32_t* rmax, int64_t* core_offsets_host);
+size_t tnb_tt_sum_round_workspace_bytes(int dtype, int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                        const int32_t* rmax);
+int tnb_tt_sum_round(int dtype, const void* const* cores_in, int noperands, const double* alpha, int ndim, const int64_t* shape,
+                     const int32_t* ranks_in, const int32_t* rmax, double eps, uint32_t flags, void* workspace,
+                     size_t workspace_bytes, void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream);
+/* Elementwise product of two TT tensors: core n of the result is the row-wise Kronecker product of the operands' cores,
+ * out[(a1 a2), i, (b1 b2)] = A[a1, i, b1] * B[a2, i, b2], written to cores_out[n] (ra_n rb_n x I_n x ra_{n+1} rb_{n+1}).
+ * Replaces: Tensor.__mul__ for TT operands (tensor.py:560-640) — with tnb_tt_round the multiply-and-round loops of
+ * metrics.hadamard_sum (metrics.py:384-446). */
+int tnb_tt_hadamard(int dtype, const void* const* cores_a, const void* const* cores_b, int ndim, const int64_t* shape,
+                    const int32_t* ranks_a, const int32_t* ranks_b, void* const* cores_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Two-factor rank-revealing split  M (m x n)  ->  left (m x r), right (r x n).
  * Replaces: tn.truncated_svd(M, delta, eps, rmax, left_ortho)  round.py:52-187.
  *   delta < 0 means "not given"; eps < 0 means "not given"; both given -> TNB_ERR_INVALID
@@ -175,6 +206,43 @@ int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int3
 size_t tnb_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r);
 int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t max_iters, void* workspace,
                size_t workspace_bytes, int32_t* index_dev, double* C_dev, int32_t* iters_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * rect_maxvol: rectangular 2-volume maximisation of each of `nbatch` tall N x r fp64 matrices (N > r).
+ * Replaces: py_rect_maxvol(A, tol, maxK, min_add_K, minK, start_maxvol_iters=10, identity_submatrix=True)
+ *           tntorch/maxvol.py:30-111 (called by tn.cross(..., _minimize=True), cross.py:399-400): maxvol with
+ *           start_maxvol_iters swaps, then rows are added while the largest squared row norm of the coefficient matrix
+ *           exceeds tol^2 (up to maxK rows) or fewer than minK rows are chosen.
+ *   index_dev nbatch x maxK int32 (device), the first K_dev[b] entries valid;  C_dev nbatch x N x maxK (device, leading
+ *   dimension maxK), the first K_dev[b] columns valid;  K_dev nbatch int32 (device).  r <= minK <= maxK <= N.
+ * ------------------------------------------------------------------------------------------ */
+size_t tnb_rect_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r, int32_t maxK);
+int tnb_rect_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t minK, int32_t maxK,
+                    int32_t start_maxvol_iters, void* workspace, size_t workspace_bytes, int32_t* index_dev, double* C_dev,
+                    int32_t* K_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched TT-cross plumbing: B independent cross problems on one grid with one rank profile advance together
+ * (tntorch_b200/cross_batch.py).  Replaces, for tensor-product grids, the per-core host work of tn.cross:
+ *   tnb_cross_gather_coords  the sample coordinates of core j — cross.py:316-321 (interface products selecting grid
+ *                            values): X[k][(b, a, i, c)] = grid[k][index_k] for the multi-index
+ *                            (lsets[b][a][0..j), i, rsets[b][c][0..N-j-1)); X is N vectors of B*Rl*I*Rr doubles
+ *   tnb_cross_update_lsets   nested left index sets after a maxvol step — cross.py:405-411; `local` = row chosen by maxvol
+ *                            in the (Rl*I) x Rn sample matrix; lnext [B][Rn][j+1]
+ *   tnb_cross_update_rsets   nested right index sets — cross.py:437-443; `local` = row in the (I*Rr) x Rp matrix;
+ *                            rprev [B][Rp][N-j]
+ *   tnb_cross_tt_eval        out[b][p] = TT_b(idx[p]) for B trains with cores [B][r][I][r'] fp64 — the validation error
+ *                            of cross.py:457-459 (Tensor.__getitem__ on a list of index vectors)
+ * All index tensors are int32 on the device; `active` (may be NULL) masks problems that already converged.
+ * ------------------------------------------------------------------------------------------ */
+int tnb_cross_gather_coords(const int32_t* lsets, const int32_t* rsets, const double* grid, int32_t Imax, int32_t B,
+                            int32_t N, int32_t j, int32_t Rl, int32_t I, int32_t Rr, double* X, void* stream);
+int tnb_cross_update_lsets(const int32_t* lsets, const int32_t* local, int32_t B, int32_t j, int32_t Rl, int32_t I,
+                           int32_t Rn, const int32_t* active, int32_t* lnext, void* stream);
+int tnb_cross_update_rsets(const int32_t* rsets, const int32_t* local, int32_t B, int32_t N, int32_t j, int32_t I,
+                           int32_t Rr, int32_t Rp, const int32_t* active, int32_t* rprev, void* stream);
+int tnb_cross_tt_eval(const double* const* cores, int32_t N, const int32_t* ranks, const int32_t* shape, const int32_t* idx,
+                      int32_t B, int32_t P, int32_t per_problem, double* out, void* stream);
 
 /* C (M x N) = A (M x K) B (K x N), all row-major, same dtype (fp32: fp32 accumulate; fp64: fp64), CUDA-core tiles.
  * Replaces: `R @ right_unfolding(next)` tensor.py:1826-1832 and `leftcoreL @ L` tensor.py:1868-1878. */

@@ -276,3 +276,31 @@ LOWNOISE_CASES = {
     "twin_lownoise_16x5_f32": dict(kind="tt_noise", shape=(16,) * 5, rank=6, noise=1e-5, seed=31, dtype="float32", ranks_tt=6),
     "smooth_24x4_f32_r5": dict(kind="smooth", shape=(24, 24, 24, 24), dtype="float32", ranks_tt=5),
 }
+
+# ---- rect_maxvol (maxvol.py:30-111): (matrix spec, keyword arguments) ----------------------------------------------------
+RECT_MAXVOL_CASES = {
+    "rect_320x10_tol1": (dict(shape=(320, 10), seed=40), dict(tol=1.0)),
+    "rect_320x10_maxK15": (dict(shape=(320, 10), seed=40), dict(tol=0.5, maxK=15)),
+    "rect_200x8_minK12": (dict(shape=(200, 8), seed=45), dict(tol=2.0, minK=12)),
+    "rect_64x6_addK": (dict(shape=(64, 6), seed=46), dict(tol=1.0, min_add_K=3, maxK=20)),
+    "rect_maxK_eq_r": (dict(shape=(320, 10), seed=40), dict(tol=1.0, maxK=10)),  # what tn.cross(_minimize=True) calls
+}
+
+# ---- batched TT-cross (BASELINE.json config 5): the family f_b(x) = 1 / (1 + b/512 + sum_i x_i) on [0, 1]^6, 32 points per
+# ---- axis, ranks_tt = 10, 3 sweeps; golden = the first 16 problems run SEQUENTIALLY by the reference from one seed ------------
+CROSS_BATCH_CASES = {
+    # default eps = 1e-6: every problem converges after the first sweep and stops there (cross.py:461-462)
+    "cfg5_default_eps": dict(N=6, I=32, lo=0.0, hi=1.0, ranks_tt=10, max_iter=3, seed=160, nproblems=16, family=512),
+    # eps = 0: all three sweeps run
+    "cfg5_three_sweeps": dict(N=6, I=32, lo=0.0, hi=1.0, ranks_tt=10, max_iter=3, eps=0.0, seed=161, nproblems=8, family=512),
+}
+
+
+def cross_family_function(b, family=512):
+    def f(*xs):
+        s = xs[0] * 0 + 1.0 + b / family
+        for x in xs:
+            s = s + x
+        return 1.0 / s
+
+    return f

@@ -124,6 +124,52 @@ def gen_maxvol():
     np.savez_compressed(os.path.join(OUT, "maxvol.npz"), **out)
 
 
+def gen_rect_maxvol():
+    from tntorch.maxvol import py_rect_maxvol as ref_rect
+
+    out = {}
+    for name, (spec, kw) in cases.RECT_MAXVOL_CASES.items():
+        A = cases.make_matrix(spec)
+        idx, C = ref_rect(A, **kw)
+        out[f"{name}/index"] = np.asarray(idx, dtype=np.int64)
+        out[f"{name}/C"] = np.asarray(C, dtype=np.float64)
+        print(name, len(idx), idx[-4:], flush=True)
+    np.savez_compressed(os.path.join(OUT, "rect_maxvol.npz"), **out)
+
+
+def gen_cross_batch():
+    """config 5: the reference has no batch mode (cross.py:256-258): B problems = B sequential calls from one seed."""
+    import time as _t
+
+    res = {}
+    torch.set_default_dtype(torch.float64)
+    for name, spec in cases.CROSS_BATCH_CASES.items():
+        np.random.seed(spec["seed"])
+        torch.manual_seed(spec["seed"])
+        domain = [torch.linspace(spec["lo"], spec["hi"], spec["I"], dtype=torch.float64) for _ in range(spec["N"])]
+        out = {"val_eps": [], "nsamples": [], "iters": [], "probe": []}
+        probe_idx = np.random.default_rng(7).integers(0, spec["I"], size=(50, spec["N"]))
+        kw = {k: spec[k] for k in ("ranks_tt", "max_iter", "eps") if k in spec}
+        t0 = _t.perf_counter()
+        for b in range(spec["nproblems"]):
+            fn = cases.cross_family_function(b, spec["family"])
+            t, info = tn.cross(fn, domain=domain, verbose=False, return_info=True, suppress_warnings=True, **kw)
+            out["val_eps"].append(float(info["val_eps"]))
+            out["nsamples"].append(int(info["nsamples"]))
+            out["iters"].append(len(info["val_epss"]))
+            out["probe"].append(t[[torch.as_tensor(probe_idx[:, k]) for k in range(spec["N"])]].torch().numpy())
+            print(name, b, float(info["val_eps"]), info["nsamples"], len(info["val_epss"]), flush=True)
+        dt = _t.perf_counter() - t0
+        res[f"{name}/val_eps"] = np.array(out["val_eps"])
+        res[f"{name}/nsamples"] = np.array(out["nsamples"])
+        res[f"{name}/iters"] = np.array(out["iters"])
+        res[f"{name}/probe"] = np.stack(out["probe"])
+        res[f"{name}/probe_idx"] = probe_idx
+        res[f"{name}/seconds_per_problem_{os.cpu_count()}cores"] = np.float64(dt / spec["nproblems"])
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "cross_batch.npz"), **res)
+
+
 def gen_cpals():
     out = {}
     for name, spec in cases.CP_CASES.items():
@@ -196,11 +242,15 @@ def gen_cross():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross", "tucker", "lownoise"]
+    which = sys.argv[1:] or ["ttsvd", "round", "tsvd", "maxvol", "cp", "cross", "tucker", "lownoise", "rect", "crossbatch"]
     if "ttsvd" in which:
         gen_ttsvd()
     if "lownoise" in which:
         gen_lownoise()
+    if "rect" in which:
+        gen_rect_maxvol()
+    if "crossbatch" in which:
+        gen_cross_batch()
     if "round" in which:
         gen_round()
     if "tsvd" in which:

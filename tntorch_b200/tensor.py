@@ -174,6 +174,54 @@ class Tensor(object):
     def __repr__(self):
         return f"{self.dim()}D TT tensor (B200): shape {list(self.shape)}, TT ranks {self.ranks_tt.tolist()}"
 
+    # ------------------------------------------------------------------ arithmetic that feeds the rounding path
+    def _tt_cores(self):
+        """This tensor as plain TT cores (Tucker factors absorbed, CP factors turned into diagonal-slice cores)."""
+        if self.batch:
+            raise NotImplementedError("arithmetic on batched tensors is not built")
+        t = self.decompress_tucker_factors() if any(U is not None for U in self.Us) else self
+        if any(c.dim() != 3 for c in t.cores):
+            t = Tensor([c for c in t.cores])
+            t._cp_to_tt()
+        return t.cores
+
+    def __add__(self, other):
+        """tensor.py:445-520 for TT operands: block cores (libtnb200 tnb_tt_sum); a scalar is added as a rank-1 term."""
+        if isinstance(other, (int, float)):
+            c0 = self.cores[0]
+            ones = [torch.ones(1, s, 1, dtype=c0.dtype, device=c0.device) for s in self.shape]
+            return Tensor(ops.tt_sum([self._tt_cores(), ones], alpha=[1.0, float(other)]))
+        return Tensor(ops.tt_sum([self._tt_cores(), other._tt_cores()]))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        if isinstance(other, (int, float)):
+            return self + (-other)
+        return Tensor(ops.tt_sum([self._tt_cores(), other._tt_cores()], alpha=[1.0, -1.0]))
+
+    def __rsub__(self, other):
+        return (-self) + other
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __mul__(self, other):
+        """scalar: the first core is scaled (like the reference); tensor: elementwise product = Kronecker cores
+        (tensor.py:560-640, libtnb200 tnb_tt_hadamard)."""
+        if isinstance(other, (int, float)):
+            cores = [c.clone() for c in self.cores]
+            cores[0] = cores[0] * other
+            return Tensor(cores, Us=[None if U is None else U.clone() for U in self.Us], batch=self.batch)
+        return Tensor(ops.tt_hadamard(self._tt_cores(), other._tt_cores()))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, (int, float)):
+            return self * (1.0 / other)
+        raise NotImplementedError("tensor / tensor needs cross-approximation (tn.cross)")
+
     # ------------------------------------------------------------------ decompression (tensor.py:1639-1687)
     def torch(self):
         if self.batch:
@@ -199,18 +247,83 @@ class Tensor(object):
     def numpy(self):
         return self.torch().detach().cpu().numpy()
 
-    # ------------------------------------------------------------------ orthogonalisation (tensor.py:1800-1909)
+    # ------------------------------------------------------------------ CP -> TT (tensor.py:1717-1762)
+    def _cp_to_tt(self, factor=None):
+        """Turn CP factors ([I, R], or [B, I, R] in a batch) into TT cores whose slices are diagonal matrices; the first
+        / last factor become [1, I, R] / [R, I, 1] (tensor.py:1717-1762).  Pure layout: no arithmetic."""
+        m = 3 if self.batch else 2
+        if factor is None:
+            if self.cores[0].dim() == m:
+                self.cores[0] = self.cores[0][:, None, ...] if self.batch else self.cores[0][None, ...]
+            for mu in range(1, self.dim() - 1):
+                self.cores[mu] = self._cp_to_tt(self.cores[mu])
+            if self.cores[-1].dim() == m:
+                self.cores[-1] = self.cores[-1].transpose(-1, -2)[..., None].contiguous()
+            return
+        if factor.dim() == m + 1:  # already a TT core
+            return factor
+        R, I = factor.shape[-1], factor.shape[-2]
+        idx = torch.arange(R, device=factor.device)
+        if self.batch:
+            core = torch.zeros(factor.shape[0], R, I, R, dtype=factor.dtype, device=factor.device)
+            core[:, idx, :, idx] = factor.permute(2, 0, 1)  # advanced indices first: [R, B, I]
+        else:
+            core = torch.zeros(R, I, R, dtype=factor.dtype, device=factor.device)
+            core[idx, :, idx] = factor.t()
+        return core
+
+    # ------------------------------------------------------------------ orthogonalisation (tensor.py:1764-1909)
+    def _samples(self):
+        """(number of samples, accessor) so that batched and plain tensors share one code path: the device kernels take
+        one problem per call or a leading batch dimension (tnb_qr_householder)."""
+        return self.cores[0].shape[0] if self.batch else 1
+
+    def factor_orthogonalize(self, mu: int):
+        """Pushes the Tucker factor's non-orthogonal part into its core (tensor.py:1771-1798): Us[mu] = Q R (device
+        Householder QR), core <- core x_mode R (library GEMM)."""
+        if self.Us[mu] is None:
+            return
+        U = self.Us[mu]
+        Q, R = ops.qr(U, return_r=True)  # batched when U is [B, I, S]
+        Q, R = Q.to(U.dtype), R.to(U.dtype)
+        self.Us[mu] = Q
+        c = self.cores[mu]
+        cp = c.dim() == (3 if self.batch else 2)
+
+        def push(core, Rm):  # core [r0, S, r1] (or CP [S, R]) with S contracted against Rm [a, S]
+            if cp:
+                return ops.matmul(Rm, core)                                        # [a, R]
+            r0, S, r1 = core.shape
+            out = ops.matmul(Rm, core.permute(1, 0, 2).reshape(S, r0 * r1))        # [a, r0 r1]
+            return out.reshape(Rm.shape[0], r0, r1).permute(1, 0, 2).contiguous()
+
+        if self.batch:
+            self.cores[mu] = torch.stack([push(c[b], R[b]) for b in range(c.shape[0])])
+        else:
+            self.cores[mu] = push(c, R)
+
     def left_orthogonalize(self, mu: int):
         """Makes the mu-th core left-orthogonal and pushes the R factor to its right core; returns R
-        (tensor.py:1800-1833).  Householder QR and the R push run in libtnb200 (tnb_qr_householder, tnb_matmul)."""
+        (tensor.py:1800-1833).  Householder QR and the R push run in libtnb200 (tnb_qr_householder, tnb_matmul);
+        CP factors are turned into TT cores first, like in the reference."""
         assert 0 <= mu < self.dim() - 1
-        if self.batch:
-            raise NotImplementedError("batched orthogonalisation is not built")
+        self.factor_orthogonalize(mu)
+        nd = 4 if self.batch else 3
+        if self.cores[mu].dim() != nd or self.cores[mu + 1].dim() != nd:
+            self._cp_to_tt()
         c = self.cores[mu]
+        nxt = self.cores[mu + 1]
+        if self.batch:
+            B = c.shape[0]
+            Q, R = ops.qr(c.reshape(B, -1, c.shape[-1]), return_r=True)  # one batched launch
+            Q, R = Q.to(c.dtype), R.to(c.dtype)
+            self.cores[mu] = Q.reshape(c.shape[:-1] + (Q.shape[2],))
+            self.cores[mu + 1] = torch.stack([ops.matmul(R[b], nxt[b].reshape(nxt.shape[1], -1)) for b in range(B)]).reshape(
+                (B, R.shape[1]) + nxt.shape[2:])
+            return R
         Q, R = ops.qr(c.reshape(-1, c.shape[-1]), return_r=True)
         Q, R = Q.to(c.dtype), R.to(c.dtype)
         self.cores[mu] = Q.reshape(c.shape[:-1] + (Q.shape[1],))
-        nxt = self.cores[mu + 1]
         self.cores[mu + 1] = ops.matmul(R, nxt.reshape(nxt.shape[0], -1)).reshape((R.shape[0],) + nxt.shape[1:])
         return R
 
@@ -218,24 +331,36 @@ class Tensor(object):
         """Makes the mu-th core right-orthogonal and pushes the L factor to its left core; returns L
         (tensor.py:1835-1879)."""
         assert 1 <= mu < self.dim()
-        if self.batch:
-            raise NotImplementedError("batched orthogonalisation is not built")
+        self.factor_orthogonalize(mu)
+        nd = 4 if self.batch else 3
+        if self.cores[mu].dim() != nd or self.cores[mu - 1].dim() != nd:
+            self._cp_to_tt()
         c = self.cores[mu]
+        prv = self.cores[mu - 1]
+        if self.batch:
+            B = c.shape[0]
+            Q, L = ops.qr(c.reshape(B, c.shape[1], -1).transpose(1, 2).contiguous(), return_r=True)
+            L, Q = L.transpose(1, 2).contiguous().to(c.dtype), Q.transpose(1, 2).contiguous().to(c.dtype)
+            self.cores[mu] = Q.reshape((B, Q.shape[1]) + c.shape[2:])
+            self.cores[mu - 1] = torch.stack([ops.matmul(prv[b].reshape(-1, prv.shape[-1]), L[b]) for b in range(B)]).reshape(
+                prv.shape[:-1] + (L.shape[2],))
+            return L
         Q, L = ops.qr(c.reshape(c.shape[0], -1).t().contiguous(), return_r=True)
         L, Q = L.t().contiguous().to(c.dtype), Q.t().contiguous().to(c.dtype)
         self.cores[mu] = Q.reshape((Q.shape[0],) + c.shape[1:])
-        prv = self.cores[mu - 1]
         self.cores[mu - 1] = ops.matmul(prv.reshape(-1, prv.shape[-1]), L).reshape(prv.shape[:-1] + (L.shape[1],))
         return L
 
     def orthogonalize(self, mu: int):
         """All left and right orthogonalisations needed to make the tensor mu-orthogonal; returns (R, L)
-        (tensor.py:1881-1909)."""
+        (tensor.py:1881-1909).  CP cores become TT cores first."""
         if mu < 0:
             mu += self.dim()
+        self._cp_to_tt()
         dt, dev = self.cores[0].dtype, self.cores[0].device
-        R = torch.ones(1, 1, dtype=dt, device=dev)
-        L = torch.ones(1, 1, dtype=dt, device=dev)
+        lead = (self.cores[0].shape[0],) if self.batch else ()
+        R = torch.ones(lead + (1, 1), dtype=dt, device=dev)
+        L = torch.ones(lead + (1, 1), dtype=dt, device=dev)
         for i in range(mu):
             R = self.left_orthogonalize(i)
         for i in range(self.dim() - 1, mu, -1):
@@ -250,6 +375,9 @@ class Tensor(object):
         if not hasattr(rmax, "__len__"):
             rmax = [rmax] * (N - 1)
         assert len(rmax) == N - 1
+        self._cp_to_tt()  # tensor.py:2031: CP (or CP-Tucker) cores become TT (or TT-Tucker) ones
+        for mu in range(N):  # orthogonalize() in the reference pushes the factors' non-orthogonal parts into the cores
+            self.factor_orthogonalize(mu)
         if self.batch:
             B = self.cores[0].shape[0]
             per = [ops.tt_round([c[b] for c in self.cores], eps=eps, rmax=rmax, batch_mode=True) for b in range(B)]
