@@ -133,6 +133,19 @@ int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t
                  const int32_t* rmax, double eps, uint32_t flags, void* workspace, size_t workspace_bytes,
                  void* cores_out, int64_t cores_capacity, int32_t* ranks_host, void* stream);
 
+/* A batch of TT tensors with ONE shape and ONE input rank profile, rounded with up to 8 of them in flight on internal
+ * streams and a single synchronisation (the batched-throughput form of BASELINE.json config 3; Tensor.round_tt on a
+ * batch=True tensor, tensor.py:2008-2083 with the leading batch dimension).  cores_in: batch * ndim device pointers,
+ * tensor-major; cores_out[i]: buffer of cores_capacity elements for tensor i (layout as tnb_tt_round); ranks_host:
+ * batch * (ndim + 1); workspace: k * per_tensor_bytes, k >= 1 tensors in flight.  Needs rank caps on every bond and
+ * full-rank left unfoldings for the in-flight path; anything else runs one tensor at a time like tnb_tt_round. */
+size_t tnb_tt_round_batch_workspace_bytes(int dtype, int batch, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                          const int32_t* rmax, size_t* per_tensor_bytes);
+int tnb_tt_round_batch(int dtype, const void* const* cores_in, int batch, int ndim, const int64_t* shape,
+                       const int32_t* ranks_in, const int32_t* rmax, double eps, uint32_t flags, void* workspace,
+                       size_t workspace_bytes, void* const* cores_out, int64_t cores_capacity, int32_t* ranks_host,
+                       int32_t* speculative_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Linear combinations of TT tensors, optionally fused with the rounding that follows them.
  * Replaces: Tensor.__add__ / __sub__ / scalar * for TT operands (tensor.py:445-520: block cores — first core side by
@@ -164,6 +177,12 @@ int tnb_tt_sum_round(int dtype, const void* const* cores_in, int noperands, cons
 int tnb_tt_hadamard(int dtype, const void* const* cores_a, const void* const* cores_b, int ndim, const int64_t* shape,
                     const int32_t* ranks_a, const int32_t* ranks_b, void* const* cores_out, void* stream);
 
+/* Measurement helper (bench.py / profiles/): dense TF32 tcgen05 peak of this GPU — one CTA per SM issuing
+ * tcgen05.mma.cta_group::1.kind::tf32 M=128 N=256 K=8 back to back on shared-memory-resident tiles (no memory traffic),
+ * `reps` commits of `per_commit` MMAs; best of `trials` launches timed with CUDA events.  The denominator of the
+ * tensor-bound roofline fractions. */
+int tnb_measure_tf32_peak(int32_t reps, int32_t per_commit, int32_t trials, double* tflops_host, double* ms_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Two-factor rank-revealing split  M (m x n)  ->  left (m x r), right (r x n).
  * Replaces: tn.truncated_svd(M, delta, eps, rmax, left_ortho)  round.py:52-187.
@@ -194,6 +213,11 @@ size_t tnb_cp_als_workspace_bytes(int dtype, int ndim, const int64_t* shape, int
 int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int32_t R, int32_t max_iter, double tol,
                void* workspace, size_t workspace_bytes, void* factors, int64_t factors_capacity, double* errors_host,
                int32_t* iters_host, void* stream);
+/* Same sweeps started from the factors already in `factors` (layout as above) instead of the HOSVD initialisation:
+ * the reference's CP on a Tucker core starts from random factors (tensor.py:278-302). */
+int tnb_cp_als_from(int dtype, const void* data, int ndim, const int64_t* shape, int32_t R, int32_t max_iter, double tol,
+                    void* workspace, size_t workspace_bytes, void* factors, int64_t factors_capacity, double* errors_host,
+                    int32_t* iters_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * maxvol: dominant r x r submatrix of each of `nbatch` tall N x r fp64 matrices (row-major, contiguous batch).

@@ -73,5 +73,5 @@ def test_reference_error_behaviour_at_the_boundary():
 
     with pytest.raises(ValueError):  # round.py:77-78
         tnb.truncated_svd(torch.zeros(3, 3), delta=1.0, eps=1.0)
-    with pytest.raises(NotImplementedError):
-        tnb.Tensor(torch.zeros(3, 3), ranks_cp=2, ranks_tucker=2)
+    with pytest.raises(ValueError):  # tensor.py:436-438 (checked before any device work)
+        tnb.Tensor([torch.zeros(2, 3, 2), torch.zeros(3, 3, 1)])  # core ranks do not match (tensor.py:177-191)

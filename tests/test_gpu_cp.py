@@ -57,3 +57,28 @@ def test_cp_als_rank_larger_than_mode():
     X = torch.einsum("ar,br,cr->abc", *fs).cuda()
     fac, info = ops.cp_als(X, 6, max_iter=60, tol=float("-inf"), return_info=True)
     assert info["errors"][-1] < 0.2
+
+
+def test_cp_on_tucker_core():
+    """tensor.py:278-302: Tensor(X, ranks_cp=R, ranks_tucker=S) = Tucker compression, then ALS on the dense Tucker core
+    from random factors; the result is a CP-Tucker tensor (cores [S_n, R], factors [I_n, S_n])."""
+    import tntorch_b200 as tnb
+
+    rng = np.random.default_rng(9)
+    fac = [rng.standard_normal((s, 3)) for s in (14, 12, 10)]
+    X = torch.as_tensor(np.einsum("ar,br,cr->abc", *fac)).cuda()
+    torch.manual_seed(0)
+    t = tnb.Tensor(X, ranks_cp=3, ranks_tucker=4, max_iter=200, tol=1e-12)
+    assert [tuple(c.shape) for c in t.cores] == [(4, 3)] * 3
+    assert [tuple(U.shape) for U in t.Us] == [(14, 4), (12, 4), (10, 4)]
+    assert list(t.shape) == [14, 12, 10]
+    err = float(torch.linalg.vector_norm(X - t.torch()) / torch.linalg.vector_norm(X))
+    assert err < 1e-3, err
+    # ops.cp_als with a given start: zero sweeps return the start itself
+    from tntorch_b200 import ops
+
+    init = [torch.as_tensor(f).cuda() for f in fac]
+    out = ops.cp_als(X, 3, max_iter=0, init=init)
+    assert all(torch.equal(a, b) for a, b in zip(out, init))
+    out, info = ops.cp_als(X, 3, max_iter=3, tol=float("-inf"), init=init, return_info=True)
+    assert info["errors"][-1] < 1e-10  # started at the exact factors: stays there

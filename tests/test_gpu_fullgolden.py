@@ -93,3 +93,40 @@ def test_cp_als_R50_matches_fp64_reference(dtype):
     err = float(torch.linalg.vector_norm(X - rec) / torch.linalg.vector_norm(X))
     ref = float(g[f"{name}/relerr"])
     assert abs(err - ref) <= 1e-5, (err, ref)
+
+
+def test_round_tt_cfg3_batch_of_64_throughput():
+    """config 3 in batch form ("single instance is latency-bound; batch shows throughput"): 64 random
+    128^10 rank-64 trains rounded to rank 16 by ONE tnb_tt_round_batch call (8 in flight, one synchronisation) against 64
+    sequential calls; every result equals the single-call result and the reference's error."""
+    import time
+
+    from tntorch_b200 import ops
+
+    g = _gold()
+    name = "cfg3_128x10_r64to16_f64"
+    spec = cases.FULL_ROUND_CASES[name]
+    base = [torch.as_tensor(c).cuda() for c in cases.make_tt(spec)]
+    B = 64
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    batch = [base] + [[torch.randn(c.shape, generator=gen, device="cuda", dtype=torch.float64) for c in base] for _ in range(B - 1)]
+    ops.tt_round_batch(batch[:8], rmax=16)  # warm-up
+    one, info1 = None, None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, info = ops.tt_round_batch(batch, rmax=16, return_info=True)
+    torch.cuda.synchronize()
+    t_batch = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    seq = [ops.tt_round(cores, rmax=16) for cores in batch[:16]]
+    torch.cuda.synchronize()
+    t_seq = (time.perf_counter() - t0) / 16
+    ncoef = sum(c.numel() for c in base)
+    print(f"round_tt 128^10 r64->16 fp64: batch of {B}: {t_batch * 1e3:.1f} ms = {t_batch / B * 1e3:.2f} ms per tensor "
+          f"({B * ncoef / t_batch / 1e9:.2f} Gcoef/s); one call at a time: {t_seq * 1e3:.2f} ms per tensor")
+    assert info["speculative"] == [1] * B
+    assert [int(c.shape[2]) for c in out[0]] == [16] * 9 + [1]
+    assert abs(_tt_relerr(base, out[0]) - float(g[f"{name}/svd/relerr"])) <= 1e-7
+    for i in (1, 7, 15):
+        assert abs(_tt_relerr(batch[i], out[i]) - _tt_relerr(batch[i], seq[i])) <= 1e-9
+    assert t_batch / B < t_seq

@@ -53,6 +53,9 @@ SIGNATURES = {
     "tnb_tt_round_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, _i32p, _i32p]),
     "tnb_tt_round": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _i64p, _i32p, _i32p, C.c_double, C.c_uint32, _vp,
                                C.c_size_t, _vp, C.c_int64, _i32p, _vp]),
+    "tnb_tt_round_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _i64p, _i32p, _i32p, C.POINTER(C.c_size_t)]),
+    "tnb_tt_round_batch": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, C.c_int, _i64p, _i32p, _i32p, C.c_double, C.c_uint32, _vp,
+                                     C.c_size_t, C.POINTER(_vp), C.c_int64, _i32p, _i32p, _vp]),
     "tnb_tt_sum_cores_capacity": (C.c_int64, [C.c_int, C.c_int, _i64p, _i32p, _i32p, _i64p]),
     "tnb_tt_sum": (C.c_int, [C.c_int, C.POINTER(_vp), C.c_int, _f64p, C.c_int, _i64p, _i32p, _vp, C.c_int64, _vp]),
     "tnb_tt_sum_round_cores_capacity": (C.c_int64, [C.c_int, C.c_int, _i64p, _i32p, _i32p, _i64p]),
@@ -67,6 +70,8 @@ SIGNATURES = {
     "tnb_cp_als_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, _i64p, C.c_int32]),
     "tnb_cp_als": (C.c_int, [C.c_int, _vp, C.c_int, _i64p, C.c_int32, C.c_int32, C.c_double, _vp, C.c_size_t, _vp, C.c_int64,
                              _f64p, _i32p, _vp]),
+    "tnb_cp_als_from": (C.c_int, [C.c_int, _vp, C.c_int, _i64p, C.c_int32, C.c_int32, C.c_double, _vp, C.c_size_t, _vp, C.c_int64,
+                                  _f64p, _i32p, _vp]),
     "tnb_maxvol_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_maxvol": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp, C.c_size_t, _vp, _vp, _i32p, _vp]),
     "tnb_rect_maxvol_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -78,6 +83,7 @@ SIGNATURES = {
     "tnb_cross_update_rsets": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
                                          _vp]),
     "tnb_cross_tt_eval": (C.c_int, [C.POINTER(_vp), C.c_int32, _i32p, _i32p, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "tnb_measure_tf32_peak": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p, _vp]),
     "tnb_matmul": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "tnb_qr_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tnb_qr_householder": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),

@@ -172,9 +172,24 @@ inline int cp_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, T* 
   return TNB_OK;
 }
 
+// acc[0] += sum x^2 (fp64)
+template <typename T>
+__global__ void cp_sumsq_kernel(const T* __restrict__ X, int64_t n, double* __restrict__ acc) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = (double)X[i];
+    s = fma(x, x, s);
+  }
+  s = block_reduce_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+// init_given: `factors` already holds the starting factors (the reference's random start of CP on a Tucker core,
+// tensor.py:278-302) and the HOSVD initialisation is skipped.
 template <typename T, class ArenaT>
 inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R, int max_iter, double tol, T* factors,
-                       double* errors_host, int32_t* iters_host, cudaStream_t st) {
+                       double* errors_host, int32_t* iters_host, cudaStream_t st, bool init_given = false) {
   const int N = d.N;
   int64_t imax = 0;
   for (int n = 0; n < N; ++n) imax = std::max<int64_t>(imax, d.shape[n]);
@@ -226,7 +241,15 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
 
   // ---------------- HOSVD initialisation (tensor.py:217-277) ----------------
   double normX2 = 0.0;
-  for (int n = 0; n < N; ++n) {
+  if (init_given) {
+    TNB_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(double), st));
+    cp_sumsq_kernel<T><<<grid_for(d.numel, 256, 1184), 256, 0, st>>>(X, d.numel, acc);
+    TNB_LAUNCH_CHECK();
+    TNB_CUDA(cudaMemcpyAsync(h, acc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(cudaStreamSynchronize(st));
+    normX2 = h[0];
+  }
+  for (int n = 0; n < N && !init_given; ++n) {
     const size_t mark = ar.off;
     const int64_t I = d.shape[n];
     GemmPlan pb = plan_batched(I, I, std::max<int64_t>(d.left[n], 1), true);

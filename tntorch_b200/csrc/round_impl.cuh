@@ -208,6 +208,225 @@ inline int tt_round_impl(ArenaT& ar, bool dry, const T* const* cores_in, const R
 }
 
 // ---------------------------------------------------------------------------------------------
+// Speculative TT rounding: both sweeps of Tensor.round_tt enqueued without a host round trip.
+//   phase A assumes every left unfolding is safely full-rank, i.e. the Cholesky-QR succeeds and keeps all rin[k+1]
+//   columns (the flag of chol_orth_kernel says otherwise); phase B assumes every rank rule returns its cap (rank caps
+//   on every bond, inactive eps budget) — spec_step_* of sweep.cuh.  ONE synchronisation at the end; a raised flag
+//   sends the tensor to the host-driven tt_round_impl.  With no host in the loop a batch of TT tensors is simply
+//   enqueued on several streams (tnb_tt_round_batch): the one-CTA Cholesky / Jacobi kernels of different tensors then
+//   run side by side on different SMs — the batched-throughput form of BASELINE.json config 3.
+// ---------------------------------------------------------------------------------------------
+__global__ void or_flag_kernel(const int* src, int* flags, int bit) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && *src) atomicOr(flags, bit);
+}
+
+template <typename T>
+inline bool tt_round_spec_eligible(const RoundDims& d, const int32_t* rmax, double eps, uint32_t flags) {
+  static const bool disabled = getenv("TNB_NO_SPECULATE") != nullptr;
+  if (disabled || (flags & TNB_FLAG_NO_SPECULATE) || d.N < 2 || !rmax) return false;
+  const double epsN = eps / std::max(1.0, std::sqrt((double)(d.N - 1)));
+  if (!(epsN * epsN < 1e-20)) return false;
+  for (int k = 0; k < d.N - 1; ++k) {
+    if (rmax[k] <= 0) return false;
+    if (d.ra[k + 1] != d.rin[k + 1] || d.ra[k] * d.shape[k] < d.rin[k + 1]) return false;  // Cholesky-QR keeps every column
+    if (d.rin[k + 1] > JACOBI_MAX_N || d.rin[k + 1] > 104) return false;                   // L, L^-1 in shared memory
+  }
+  for (int mu = d.N - 1; mu >= 1; --mu)
+    if (!spec_step_ok<T>(d.ra[mu], d.shape[mu] * d.rcap[mu + 1], d.rcap[mu], false)) return false;
+  return true;
+}
+
+template <typename T, class ArenaT>
+inline int tt_round_spec_enqueue(ArenaT& ar, bool dry, const T* const* cores_in, const RoundDims& d, const int32_t* rmax,
+                                 double eps, uint32_t flags, T* cores_out, SpecHostBack* hb, cudaStream_t st) {
+  const int N = d.N;
+  StepCtx cx;
+  cx.flags = flags;
+  cx.allow_tc = false;
+  cx.st = st;
+  const double epsN = eps / std::max(1.0, std::sqrt((double)(N - 1)));
+  cx.eps_scaled2 = epsN * epsN;
+  cx.sc = ar.template take<SweepScalars>(1);
+  cx.d_flags = ar.template take<int>(4);
+  cx.d_ranks = ar.template take<int32_t>(N + 1);
+  int* d_chol = ar.template take<int>(4);
+  size_t maxcore = 0;
+  for (int k = 0; k < N; ++k) maxcore = std::max<size_t>(maxcore, (size_t)d.ra[k] * d.shape[k] * d.rin[k + 1]);
+  T* cur = ar.template take<T>(maxcore);
+  T* nxt = ar.template take<T>(maxcore);
+  std::vector<T*> Q(N, nullptr);
+  for (int k = 0; k < N; ++k) Q[k] = ar.template take<T>((size_t)d.ra[k] * d.shape[k] * std::max<int64_t>(d.ra[k + 1], 1));
+  size_t peak = ar.off;
+  if (!dry) {
+    TNB_CUDA(cudaMemsetAsync(cx.d_flags, 0, 4 * sizeof(int), st));
+    TNB_CUDA(cudaMemsetAsync(d_chol, 0, 4 * sizeof(int), st));
+    TNB_CUDA(cudaMemcpyAsync(cur, cores_in[0], sizeof(T) * (size_t)d.shape[0] * d.rin[1], cudaMemcpyDeviceToDevice, st));
+  }
+  // ---------------- phase A ----------------
+  for (int k = 0; k < N - 1; ++k) {
+    const size_t mark = ar.off;
+    const int64_t rowsA = d.ra[k] * d.shape[k];
+    const int64_t cols = d.rin[k + 1];
+    GemmPlan pl = plan_gemm(cols, cols, rowsA, true);
+    double* partial = ar.template take<double>(pl.partial_elems);
+    double* G = ar.template take<double>((size_t)cols * cols);
+    double* js = ar.template take<double>((size_t)2 * cols * (cols | 1));
+    T* fac = ar.template take<T>((size_t)cols * cols);
+    T* Rf = ar.template take<T>((size_t)cols * cols);
+    if (ar.off > peak) peak = ar.off;
+    if (!dry) {
+      if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tt_round: workspace too small (need > %zu bytes)", ar.off);
+      TNB_TRY((gemm_splitk<T, T, double, double, float>(pl, cols, cols, rowsA, cur, cols, false, cur, cols, false, partial, G,
+                                                        cols, 1.0, nullptr, 0, 0.0, nullptr, 0, 0.0, true, (float*)nullptr, 0,
+                                                        st)));
+      const size_t csm = (size_t)2 * cols * (cols | 1) * sizeof(double);
+      static PerDeviceFlag attr_done;
+      TNB_CUDA(ensure_dyn_smem(attr_done, chol_orth_kernel<T>, 180 * 1024));
+      chol_orth_kernel<T><<<1, 1024, csm, st>>>(G, (int)cols, js, fac, d_chol, 1, Rf);
+      TNB_LAUNCH_CHECK();
+      TNB_TRY((gemm_direct<T, T, T, T>(rowsA, cols, cols, cur, cols, true, fac, cols, false, Q[k], cols, (T)1, nullptr, 0,
+                                       (T)0, nullptr, 0, (T)0, st)));
+      const int64_t ncols = d.shape[k + 1] * d.rin[k + 2];
+      TNB_TRY((gemm_direct<T, T, T, T>(cols, ncols, cols, Rf, cols, true, cores_in[k + 1], ncols, false, nxt, ncols, (T)1,
+                                       nullptr, 0, (T)0, nullptr, 0, (T)0, st)));
+      T* t = cur; cur = nxt; nxt = t;
+    }
+    ar.off = mark;
+  }
+  if (!dry) {
+    or_flag_kernel<<<1, 32, 0, st>>>(d_chol, cx.d_flags, 64);
+    TNB_LAUNCH_CHECK();
+  }
+  // ---------------- phase B ----------------
+  const T* M = cur;
+  T* left = nxt;
+  SpecStep<T> step;
+  for (int mu = N - 1, t = 0; mu >= 1; --mu, ++t) {
+    const size_t mark = ar.off;
+    const int64_t rows = d.ra[mu];
+    const int64_t n = d.shape[mu] * d.rcap[mu + 1];
+    spec_step_carve<T>(ar, cx, rows, n, d.rcap[mu], step);
+    if (ar.off > peak) peak = ar.off;
+    if (!dry) {
+      if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tt_round: workspace too small (need > %zu bytes)", ar.off);
+      TNB_TRY(spec_step_gram<T>(cx, M, rows, n, t == 0, step, false));
+      TNB_TRY(spec_step_rest<T>(cx, M, rows, n, rmax[mu - 1], cores_out + d.slot[mu], left, mu, step, false));
+      const int64_t rank = d.rcap[mu];
+      const int64_t rowsP = d.ra[mu - 1] * d.shape[mu - 1];
+      T* dst = (mu - 1 == 0) ? cores_out + d.slot[0] : cur;
+      TNB_TRY((gemm_direct<T, T, T, T>(rowsP, rank, rows, Q[mu - 1], rows, true, left, rank, false, dst, rank, (T)1, nullptr,
+                                       0, (T)0, nullptr, 0, (T)0, st)));
+      M = dst;
+    }
+    ar.off = mark;
+  }
+  if (dry) {
+    ar.off = peak;
+    return TNB_OK;
+  }
+  TNB_CUDA(cudaMemcpyAsync(&hb->sc, cx.sc, sizeof(SweepScalars), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(cudaMemcpyAsync(hb->flags, cx.d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return TNB_OK;
+}
+
+inline void tt_round_spec_ranks(const RoundDims& d, int32_t* ranks_host) {
+  ranks_host[0] = 1;
+  ranks_host[d.N] = 1;
+  for (int mu = 1; mu < d.N; ++mu) ranks_host[mu] = (int32_t)d.rcap[mu];
+}
+
+// Dispatcher: speculative rounding when eligible, host-driven rounding otherwise and as the fallback.
+template <typename T, class ArenaT>
+inline int tt_round_any(ArenaT& ar, bool dry, const T* const* cores_in, const RoundDims& d, const int32_t* rmax, double eps,
+                        uint32_t flags, T* cores_out, int32_t* ranks_host, cudaStream_t st, int* speculative_out = nullptr) {
+  const size_t base = ar.off;
+  if (speculative_out) *speculative_out = 0;
+  if (dry) {
+    size_t need = 0;
+    bool caps = rmax != nullptr && d.N >= 2;
+    for (int k = 0; caps && k < d.N - 1; ++k) caps = rmax[k] > 0 && d.rin[k + 1] <= 104;
+    if (caps) {
+      const int rc = tt_round_spec_enqueue<T>(ar, true, cores_in, d, rmax, eps, flags, cores_out, nullptr, st);
+      if (rc == TNB_OK) need = ar.off - base;
+      ar.off = base;
+    }
+    const int rc = tt_round_impl<T>(ar, true, cores_in, d, rmax, eps, flags, cores_out, ranks_host, st);
+    if (rc == TNB_OK && need > ar.off - base) ar.off = base + need;
+    return rc;
+  }
+  if (tt_round_spec_eligible<T>(d, rmax, eps, flags)) {
+    SpecHostBack* hb = static_cast<SpecHostBack*>(pinned_scratch(sizeof(SpecHostBack)));
+    if (!hb) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
+    const int rc = tt_round_spec_enqueue<T>(ar, false, cores_in, d, rmax, eps, flags, cores_out, hb, st);
+    TNB_CUDA(cudaStreamSynchronize(st));
+    if (rc == TNB_OK && hb->flags[0] == 0) {
+      tt_round_spec_ranks(d, ranks_host);
+      if (speculative_out) *speculative_out = 1;
+      return TNB_OK;
+    }
+    if (rc != TNB_OK && rc != TNB_ERR_UNSUPPORTED) return rc;
+    ar.off = base;
+    ar.ok = true;
+  }
+  return tt_round_impl<T>(ar, false, cores_in, d, rmax, eps, flags, cores_out, ranks_host, st);
+}
+
+// A batch of TT tensors with one rank profile: every tensor's two sweeps on its own internal stream, one synchronisation.
+template <typename T>
+inline int tt_round_batch_impl(void* workspace, size_t per_tensor_bytes, int inflight, const T* const* cores_in /* [B][N] */,
+                               int batch, const RoundDims& d, const int32_t* rmax, double eps, uint32_t flags,
+                               T* const* cores_out, int32_t* ranks_host, int32_t* spec_host, cudaStream_t st) {
+  const int N = d.N;
+  char* ws = static_cast<char*>(workspace);
+  const bool spec = batch > 1 && inflight > 1 && tt_round_spec_eligible<T>(d, rmax, eps, flags);
+  if (!spec) {
+    for (int i = 0; i < batch; ++i) {
+      Arena ar(ws, per_tensor_bytes);
+      int sp = 0;
+      TNB_TRY((tt_round_any<T, Arena>(ar, false, cores_in + (size_t)i * N, d, rmax, eps, flags, cores_out[i],
+                                      ranks_host + (size_t)i * (N + 1), st, &sp)));
+      if (spec_host) spec_host[i] = sp;
+    }
+    return TNB_OK;
+  }
+  if (inflight > TNB_BATCH_MAX_INFLIGHT) inflight = TNB_BATCH_MAX_INFLIGHT;
+  if (inflight > batch) inflight = batch;
+  StreamPool& pool = StreamPool::get();
+  std::lock_guard<std::mutex> lk(pool.mu);
+  TNB_TRY(pool.ensure());
+  SpecHostBack* hbs = static_cast<SpecHostBack*>(pinned_scratch((size_t)batch * sizeof(SpecHostBack)));
+  if (!hbs) return fail(TNB_ERR_CUDA, "pinned scratch allocation failed");
+  TNB_CUDA(cudaEventRecord(pool.ev[TNB_BATCH_MAX_INFLIGHT], st));
+  for (int s = 0; s < inflight; ++s) TNB_CUDA(cudaStreamWaitEvent(pool.st[s], pool.ev[TNB_BATCH_MAX_INFLIGHT], 0));
+  int rc = TNB_OK;
+  for (int i = 0; i < batch && rc == TNB_OK; ++i) {
+    const int s = i % inflight;  // tensor i + inflight reuses workspace slice s on the same stream: ordered
+    Arena ar(ws + (size_t)s * per_tensor_bytes, per_tensor_bytes);
+    rc = tt_round_spec_enqueue<T>(ar, false, cores_in + (size_t)i * N, d, rmax, eps, flags, cores_out[i], hbs + i, pool.st[s]);
+  }
+  for (int s = 0; s < inflight; ++s) {
+    cudaEventRecord(pool.ev[s], pool.st[s]);
+    cudaStreamWaitEvent(st, pool.ev[s], 0);
+  }
+  TNB_CUDA(cudaStreamSynchronize(st));
+  if (rc != TNB_OK && rc != TNB_ERR_UNSUPPORTED) return rc;
+  std::vector<int> bad(batch, 0);
+  for (int i = 0; i < batch; ++i) bad[i] = (rc != TNB_OK) || hbs[i].flags[0] != 0;
+  for (int i = 0; i < batch; ++i) {
+    int32_t* rk = ranks_host + (size_t)i * (N + 1);
+    if (!bad[i]) {
+      tt_round_spec_ranks(d, rk);
+      if (spec_host) spec_host[i] = 1;
+      continue;
+    }
+    Arena ar(ws, per_tensor_bytes);
+    TNB_TRY((tt_round_impl<T, Arena>(ar, false, cores_in + (size_t)i * N, d, rmax, eps, flags, cores_out[i], rk, st)));
+    if (spec_host) spec_host[i] = 0;
+  }
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // sum_k alpha_k T_k in TT format: block cores (tensor.py:445-520, Tensor.__add__ for TT operands — first core: blocks side
 // by side, last core: blocks stacked, interior cores: block diagonal), assembled by ONE kernel per core straight into the
 // buffer the rounding sweep reads, so that the `tn.round(a + b)` of tools.reduce (tools.py:460-512) is a single library call

@@ -13,6 +13,7 @@
 #include "maxvol.cuh"
 #include "qr.cuh"
 #include "cross_kernels.cuh"
+#include "peak_tf32.cuh"
 
 using namespace tnb;
 
@@ -193,9 +194,9 @@ size_t tnb_tt_round_workspace_bytes(int dtype, int ndim, const int64_t* shape, c
   ArenaSizer ar;
   int rc;
   if (dtype == TNB_F32)
-    rc = tt_round_impl<float>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
+    rc = tt_round_any<float>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
   else
-    rc = tt_round_impl<double>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
+    rc = tt_round_any<double>(ar, true, nullptr, d, rmax, 0.0, 0, nullptr, nullptr, 0);
   if (rc != TNB_OK) return 0;
   return with_slack(ar.off);
 }
@@ -214,10 +215,42 @@ int tnb_tt_round(int dtype, const void* const* cores_in, int ndim, const int64_t
                 (long long)cores_capacity, (long long)d.capacity);
   Arena ar(workspace, workspace_bytes);
   if (dtype == TNB_F32)
-    return tt_round_impl<float>(ar, false, reinterpret_cast<const float* const*>(cores_in), d, rmax, eps, flags,
-                                static_cast<float*>(cores_out), ranks_host, as_stream(stream));
-  return tt_round_impl<double>(ar, false, reinterpret_cast<const double* const*>(cores_in), d, rmax, eps, flags,
-                               static_cast<double*>(cores_out), ranks_host, as_stream(stream));
+    return tt_round_any<float>(ar, false, reinterpret_cast<const float* const*>(cores_in), d, rmax, eps, flags,
+                               static_cast<float*>(cores_out), ranks_host, as_stream(stream));
+  return tt_round_any<double>(ar, false, reinterpret_cast<const double* const*>(cores_in), d, rmax, eps, flags,
+                              static_cast<double*>(cores_out), ranks_host, as_stream(stream));
+}
+
+size_t tnb_tt_round_batch_workspace_bytes(int dtype, int batch, int ndim, const int64_t* shape, const int32_t* ranks_in,
+                                          const int32_t* rmax, size_t* per_tensor_bytes) {
+  const size_t one = tnb_tt_round_workspace_bytes(dtype, ndim, shape, ranks_in, rmax);
+  if (per_tensor_bytes) *per_tensor_bytes = one;
+  if (one == 0 || batch < 1) return 0;
+  return one * (size_t)(batch < TNB_BATCH_MAX_INFLIGHT ? batch : TNB_BATCH_MAX_INFLIGHT);
+}
+
+int tnb_tt_round_batch(int dtype, const void* const* cores_in, int batch, int ndim, const int64_t* shape,
+                       const int32_t* ranks_in, const int32_t* rmax, double eps, uint32_t flags, void* workspace,
+                       size_t workspace_bytes, void* const* cores_out, int64_t cores_capacity, int32_t* ranks_host,
+                       int32_t* speculative_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (batch < 0 || (batch > 0 && (!cores_in || !cores_out)) || !shape || !ranks_in || !ranks_host || !workspace)
+    return fail(TNB_ERR_INVALID, "tnb_tt_round_batch: null argument");
+  RoundDims d;
+  TNB_TRY(make_round_dims(ndim, shape, ranks_in, rmax, d));
+  if (cores_capacity < d.capacity) return fail(TNB_ERR_WORKSPACE, "tnb_tt_round_batch: cores buffers too small");
+  const size_t one = tnb_tt_round_workspace_bytes(dtype, ndim, shape, ranks_in, rmax);
+  if (one == 0) return fail(TNB_ERR_UNSUPPORTED, "tnb_tt_round_batch: unsupported shape");
+  if (workspace_bytes < one) return fail(TNB_ERR_WORKSPACE, "tnb_tt_round_batch: workspace %zu < %zu", workspace_bytes, one);
+  const int inflight = (int)std::min<size_t>(workspace_bytes / one, (size_t)TNB_BATCH_MAX_INFLIGHT);
+  if (dtype == TNB_F32)
+    return tt_round_batch_impl<float>(workspace, one, inflight, reinterpret_cast<const float* const*>(cores_in), batch, d, rmax,
+                                      eps, flags, reinterpret_cast<float* const*>(cores_out), ranks_host, speculative_host,
+                                      as_stream(stream));
+  return tt_round_batch_impl<double>(workspace, one, inflight, reinterpret_cast<const double* const*>(cores_in), batch, d, rmax,
+                                     eps, flags, reinterpret_cast<double* const*>(cores_out), ranks_host, speculative_host,
+                                     as_stream(stream));
 }
 
 // ------------------------------------------------------------------ sums of TT tensors (+ fused rounding)
@@ -395,6 +428,25 @@ int tnb_cp_als(int dtype, const void* data, int ndim, const int64_t* shape, int3
                              static_cast<double*>(factors), errors_host, iters_host, as_stream(stream));
 }
 
+int tnb_cp_als_from(int dtype, const void* data, int ndim, const int64_t* shape, int32_t R, int32_t max_iter, double tol,
+                    void* workspace, size_t workspace_bytes, void* factors, int64_t factors_capacity, double* errors_host,
+                    int32_t* iters_host, void* stream) {
+  TNB_TRY(check_dtype(dtype));
+  TNB_TRY(require_device());
+  if (!data || !shape || !workspace || !factors) return fail(TNB_ERR_INVALID, "tnb_cp_als_from: null argument");
+  if (max_iter < 0) return fail(TNB_ERR_INVALID, "tnb_cp_als_from: max_iter < 0");
+  CpDims d;
+  TNB_TRY(make_cp_dims(ndim, shape, R, d));
+  if (factors_capacity < d.ftotal) return fail(TNB_ERR_WORKSPACE, "tnb_cp_als_from: factor buffer too small");
+  Arena ar(workspace, workspace_bytes);
+  if (dtype == TNB_F32)
+    return cp_als_impl<float>(ar, false, static_cast<const float*>(data), d, R, max_iter, tol,
+                              static_cast<float*>(factors), errors_host, iters_host, as_stream(stream), true);
+  return cp_als_impl<double>(ar, false, static_cast<const double*>(data), d, R, max_iter, tol,
+                             static_cast<double*>(factors), errors_host, iters_host, as_stream(stream), true);
+}
+
+
 // ------------------------------------------------------------------ maxvol
 size_t tnb_maxvol_workspace_bytes(int32_t nbatch, int32_t N, int32_t r) {
   if (nbatch < 1 || N < 1 || r < 1) return 0;
@@ -474,6 +526,12 @@ int tnb_cross_tt_eval(const double* const* cores, int32_t N, const int32_t* rank
   cross_tt_eval_kernel<<<grid_for((int64_t)B * P, 128), 128, 0, as_stream(stream)>>>(a, idx, B, P, per_problem, out);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
+}
+
+int tnb_measure_tf32_peak(int32_t reps, int32_t per_commit, int32_t trials, double* tflops_host, double* ms_host, void* stream) {
+  TNB_TRY(require_device());
+  if (!tflops_host || reps < 1 || per_commit < 1 || trials < 1) return fail(TNB_ERR_INVALID, "tnb_measure_tf32_peak: bad argument");
+  return measure_tf32_peak(reps, per_commit, trials, tflops_host, ms_host, as_stream(stream));
 }
 
 int tnb_matmul(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, void* stream) {

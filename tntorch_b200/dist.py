@@ -98,7 +98,15 @@ def round_tt_batch_sharded(tts: Sequence[Sequence[torch.Tensor]], rmax=None, eps
     """config 3 in batch form: a list of TT tensors (lists of cores), each rounded on the rank that owns it."""
     from . import ops
 
-    return batch_sharded(tts, lambda cores: ops.tt_round(list(cores), eps=eps, rmax=rmax), gather)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(len(tts), world, rank)
+    same = hi > lo and all([c.shape for c in tts[i]] == [c.shape for c in tts[lo]] for i in range(lo, hi))
+    if same:  # one library call for the local shard, several tensors in flight (tnb_tt_round_batch)
+        local = ops.tt_round_batch([list(tts[i]) for i in range(lo, hi)], eps=eps, rmax=rmax)
+    else:
+        local = [ops.tt_round(list(tts[i]), eps=eps, rmax=rmax) for i in range(lo, hi)]
+    return all_gather_cores(local, len(tts)) if gather else local
 
 
 def cp_als_batch_sharded(tensors: Sequence[torch.Tensor], R: int, max_iter: int = 25, tol: float = 1e-4, gather: bool = True):

@@ -64,6 +64,13 @@ def set_reserved_sms(n: int) -> None:
     lib().tnb_set_reserved_sms(int(n))
 
 
+def measure_tf32_peak(reps: int = 200, per_commit: int = 64, trials: int = 5):
+    """Dense TF32 tcgen05 peak of the current GPU in TFLOP/s (csrc/peak_tf32.cuh)."""
+    tf, ms = (C.c_double * 1)(), (C.c_double * 1)()
+    check(lib().tnb_measure_tf32_peak(int(reps), int(per_commit), int(trials), tf, ms, _stream()))
+    return float(tf[0]), float(ms[0])
+
+
 def has_tensorcore_path() -> bool:
     return bool(lib().tnb_has_tensorcore_path())
 
@@ -308,6 +315,53 @@ def tt_round(cores: Sequence[torch.Tensor], eps: float = 1e-14, rmax=None, batch
     return res
 
 
+def tt_round_batch(batch_cores: Sequence[Sequence[torch.Tensor]], eps: float = 1e-14, rmax=None, batch_mode: bool = False,
+                   inflight: int = 8, return_info: bool = False):
+    """Round a batch of TT tensors that share shape and input ranks: ONE library call, several tensors in flight
+    (tnb_tt_round_batch).  batch_cores: per tensor, its list of cores [r, I, r'].  Returns per tensor the new cores."""
+    B = len(batch_cores)
+    if B == 0:
+        return []
+    N = len(batch_cores[0])
+    dt, dev = batch_cores[0][0].dtype, batch_cores[0][0].device
+    cs = [[c.contiguous() for c in cores] for cores in batch_cores]
+    shape = [c.shape[1] for c in cs[0]]
+    rin = [cs[0][0].shape[0]] + [c.shape[2] for c in cs[0]]
+    for cores in cs:
+        if [c.shape for c in cores] != [c.shape for c in cs[0]]:
+            raise ValueError("tt_round_batch: all tensors must share their core shapes")
+    code = _DT[dt]
+    rm = _rmax_list(rmax, max(N - 1, 0))
+    L = lib()
+    sh, rinc = i64(shape), i32(rin)
+    rmc = i32(rm) if N > 1 else i32([0])
+    offs = (C.c_int64 * N)()
+    cap = L.tnb_tt_round_cores_capacity(N, sh, rinc, rmc, offs)
+    one = C.c_size_t(0)
+    total = L.tnb_tt_round_batch_workspace_bytes(code, B, N, sh, rinc, rmc, C.byref(one))
+    if cap < 0 or one.value == 0:
+        check(_lib.ERR_UNSUPPORTED)
+    k = max(1, min(int(inflight), B, 8))
+    ws = _ws(one.value * k, dev)
+    out = torch.empty(B, int(cap), dtype=dt, device=dev)
+    ranks = (C.c_int32 * (B * (N + 1)))()
+    spec = (C.c_int32 * B)()
+    pin = (C.c_void_p * (B * N))(*[c.data_ptr() for cores in cs for c in cores])
+    pout = (C.c_void_p * B)(*[out[i].data_ptr() for i in range(B)])
+    flags = _lib.FLAG_BATCH_MODE if batch_mode else 0
+    with torch.cuda.device(dev):
+        check(L.tnb_tt_round_batch(code, pin, B, N, sh, rinc, rmc, float(eps), flags, _ptr(ws), ws.numel(), pout, cap, ranks, spec,
+                                   _stream()))
+    res = []
+    for i in range(B):
+        base = i * (N + 1)
+        res.append([out[i, offs[n]: offs[n] + ranks[base + n] * shape[n] * ranks[base + n + 1]].view(ranks[base + n], shape[n], ranks[base + n + 1])
+                    for n in range(N)])
+    if return_info:
+        return res, dict(speculative=[int(x) for x in spec])
+    return res
+
+
 def _tt_operands(operands):
     """operands: list of lists of TT cores [r, I, r'] (same shape, dtype, device) -> pointers / ranks for the C-ABI."""
     K = len(operands)
@@ -418,9 +472,10 @@ def truncated_svd(M: torch.Tensor, delta=None, eps=None, rmax=None, left_ortho=T
     return out + (rank[0] < 0,) if return_zero_flag else out
 
 
-def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, return_info: bool = False):
+def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, return_info: bool = False, init=None):
     """CP-ALS on the device (tn.Tensor(data, ranks_cp=R, max_iter=, tol=), tensor.py:210-400).
-    Returns the list of factor matrices [I_n, R]."""
+    Returns the list of factor matrices [I_n, R].  init: optional list of starting factors [I_n, R] (CP on a Tucker
+    core starts from random factors, tensor.py:278-302); default: the HOSVD initialisation of tensor.py:217-277."""
     _require_cuda(data, "cp_als")
     data = data.contiguous()
     code = _dtype_code(data)
@@ -436,12 +491,19 @@ def cp_als(data: torch.Tensor, R: int, max_iter: int = 25, tol: float = 1e-4, re
     if wsb == 0:
         check(_lib.ERR_UNSUPPORTED)
     ws = _ws(wsb, data.device)
-    fac = torch.empty(int(cap), dtype=data.dtype, device=data.device)
+    fac = torch.zeros(int(cap), dtype=data.dtype, device=data.device)
     errs = (C.c_double * max(int(max_iter), 1))()
     iters = (C.c_int32 * 1)()
+    entry = L.tnb_cp_als
+    if init is not None:
+        assert len(init) == N
+        for n in range(N):
+            assert tuple(init[n].shape) == (shape[n], int(R))
+            fac[offs[n]: offs[n] + shape[n] * R].copy_(init[n].to(device=data.device, dtype=data.dtype).reshape(-1))
+        entry = L.tnb_cp_als_from
     with torch.cuda.device(data.device):
-        check(L.tnb_cp_als(code, _ptr(data), N, sh, int(R), int(max_iter), float(tol), _ptr(ws), ws.numel(), _ptr(fac), cap,
-                           errs, iters, _stream()))
+        check(entry(code, _ptr(data), N, sh, int(R), int(max_iter), float(tol), _ptr(ws), ws.numel(), _ptr(fac), cap,
+                    errs, iters, _stream()))
     factors = [fac[offs[n]: offs[n] + shape[n] * R].view(shape[n], R) for n in range(N)]
     if return_info:
         return factors, dict(errors=[errs[i] for i in range(iters[0])], iters=int(iters[0]))

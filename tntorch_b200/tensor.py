@@ -48,8 +48,6 @@ class Tensor(object):
     ):
         assert algorithm in ("svd", "eig")  # both map onto the same Gram/eigen kernels
         self.batch = batch
-        if ranks_tucker is not None and ranks_cp is not None:
-            raise NotImplementedError("CP on a Tucker core (tensor.py:278-302) is not built")
         if isinstance(data, (list, tuple)):  # explicit cores (tensor.py:163-192)
             min_dim, max_dim = (3, 4) if batch else (2, 3)
             if not all(min_dim <= d.dim() <= max_dim for d in data):
@@ -83,7 +81,19 @@ class Tensor(object):
                 assert not hasattr(ranks_cp, "__len__")
                 if eps is not None:
                     raise ValueError("Specify eps or ranks, but not both")
-                if batch:
+                if ranks_tucker is not None:
+                    # CP on Tucker's core (tensor.py:278-302): exact TT -> round_tucker(rmax=ranks_tucker) -> the dense
+                    # Tucker core -> ALS from RANDOM factors (torch.randn, like the reference); the Tucker factors stay
+                    if batch:
+                        raise NotImplementedError("batched CP on a Tucker core is not built")
+                    self.cores = ops.ttsvd(data, rmax=None, eps=0.0)
+                    self.Us = [None] * N
+                    self.round_tucker(rmax=ranks_tucker, algorithm=algorithm)
+                    core = self.tucker_core().contiguous()
+                    init = [torch.randn(sh, ranks_cp, dtype=core.dtype, device=dev) for sh in core.shape]
+                    self.cores = ops.cp_als(core, ranks_cp, max_iter=max_iter, tol=tol, init=init)
+                    Us = self.Us
+                elif batch:
                     self.cores = [torch.stack(f, dim=0) for f in zip(*[
                         ops.cp_als(data[b], ranks_cp, max_iter=max_iter, tol=tol) for b in range(data.shape[0])])]
                 else:
@@ -152,6 +162,8 @@ class Tensor(object):
         for c, U in zip(self.cores, self.Us):
             if U is None:
                 cores.append(c)
+            elif c.dim() == 2:  # CP factor [S, R] under a Tucker factor [I, S]
+                cores.append(ops.matmul(U, c.contiguous()))
             else:
                 r0, S, r1 = c.shape
                 m = ops.matmul(U, c.permute(1, 0, 2).reshape(S, r0 * r1))  # [I, r0*r1]
@@ -380,7 +392,7 @@ class Tensor(object):
             self.factor_orthogonalize(mu)
         if self.batch:
             B = self.cores[0].shape[0]
-            per = [ops.tt_round([c[b] for c in self.cores], eps=eps, rmax=rmax, batch_mode=True) for b in range(B)]
+            per = ops.tt_round_batch([[c[b] for c in self.cores] for b in range(B)], eps=eps, rmax=rmax, batch_mode=True)
             self.cores = [torch.stack([p[k] for p in per], dim=0) for k in range(N)]
         else:
             self.cores = ops.tt_round(self.cores, eps=eps, rmax=rmax)
