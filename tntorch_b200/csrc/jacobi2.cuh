@@ -206,6 +206,119 @@ __global__ void __launch_bounds__(1024) jacobi2_eigh_kernel(const double* __rest
   if (tid == 0 && info) info[0] = s_sweeps;
 }
 
+// fp64 results at mostly fp32 cost.  The B200 issues ~16 fp64 FMAs per clock and SM against 128 fp32 ones, and a 64 x 64
+// fp64 Jacobi solve is bound by exactly that (measured 0.88 ms, nine sweeps).  Here the sweeps that do the real work run
+// in fp32; their basis V is promoted, re-orthonormalised in fp64 (one Newton-Schulz step: 1e-7 -> 1e-14), the matrix is
+// taken into that basis in fp64, S2 = V^T G V — now diagonal up to ~1e-6 — and fp64 sweeps finish from there: two of them
+// by quadratic convergence (1e-6 -> 1e-12 -> below the threshold).  Same contract and accuracy as the all-fp64 kernel.
+constexpr int JAC2_MIXED_MAX_N = 64;
+
+__global__ void __launch_bounds__(1024) jacobi2_mixed_kernel(const double* __restrict__ Gin, int n, int ldg,
+                                                             double* __restrict__ w_out, double* __restrict__ V_out,
+                                                             int max_sweeps, double tol, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char jac2m_smem[];
+  __shared__ double s_w[JAC2_MAX_N + 2];
+  __shared__ int s_rank[JAC2_MAX_N + 2];
+  __shared__ double s_gmax;
+  __shared__ int s_sweeps32, s_sweeps64;
+  Jac2<double> J;
+  Jac2<float> F;
+  jac2_carve<double>(jac2m_smem, n, tol, J);
+  jac2_carve<float>(jac2m_smem + jac2_smem_bytes<double>(n), n, 2e-6f, F);
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int np = J.np, lds = J.lds;
+  double dmax = 0.0;
+  for (int i = tid; i < n; i += nt) dmax = fmax(dmax, fabs(Gin[(size_t)i * ldg + i]));
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (tid == 0) s_gmax = 0.0;
+  __syncthreads();
+  if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&s_gmax), (unsigned long long)__double_as_longlong(dmax));
+  __syncthreads();
+  const double gscale = s_gmax > 0.0 ? s_gmax : 1.0;
+  const double ginv = 1.0 / gscale;
+  // ---- fp32 solve ----
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int r = idx / np, c = idx - r * np;
+    double v = 0.0;
+    if (r < n && c < n) v = 0.5 * (Gin[(size_t)r * ldg + c] + Gin[(size_t)c * ldg + r]) * ginv;
+    if (c >= r) F.S[0][r * lds + c] = (float)v;
+    F.V[0][r * lds + c] = (r == c) ? 1.f : 0.f;
+    J.S[1][r * lds + c] = v;  // the scaled symmetric matrix in fp64 (full storage), read by the congruence below
+  }
+  __syncthreads();
+  const int c32 = jac2_solve(F, max_sweeps, &s_sweeps32);
+  const float* V32 = F.V[c32];
+  // ---- promote, re-orthonormalise (fp64 Newton-Schulz), congruence ----
+  double* Vp = J.V[1];   // promoted basis
+  double* E = J.S[0];    // 1.5 I - 0.5 V^T V (full storage), later overwritten by S2
+  double* Vn = J.V[0];   // orthonormal basis the fp64 sweeps start from
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int r = idx / np, c = idx - r * np;
+    Vp[r * lds + c] = (double)V32[r * lds + c];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int i = idx / np, j = idx - i * np;
+    double acc = 0.0;
+    for (int c = 0; c < np; ++c) acc = fma(Vp[c * lds + i], Vp[c * lds + j], acc);
+    E[i * lds + j] = (i == j ? 1.5 : 0.0) - 0.5 * acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int i = idx / np, j = idx - i * np;
+    double acc = 0.0;
+    for (int c = 0; c < np; ++c) acc = fma(Vp[i * lds + c], E[c * lds + j], acc);
+    Vn[i * lds + j] = acc;
+  }
+  __syncthreads();
+  // W = G Vn into Vp (the promoted copy is dead), then S2 = Vn^T W (upper triangle) into S[0]
+  const double* Gs = J.S[1];
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int i = idx / np, j = idx - i * np;
+    double acc = 0.0;
+    for (int c = 0; c < np; ++c) acc = fma(Gs[i * lds + c], Vn[c * lds + j], acc);
+    Vp[i * lds + j] = acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < np * np; idx += nt) {
+    const int i = idx / np, j = idx - i * np;
+    if (j < i) continue;
+    double acc = 0.0;
+    for (int c = 0; c < np; ++c) acc = fma(Vn[c * lds + i], Vp[c * lds + j], acc);
+    E[i * lds + j] = acc;  // E == J.S[0]
+  }
+  __syncthreads();
+  // ---- fp64 finish (V[0] = Vn is the starting basis) ----
+  const int cur = jac2_solve(J, max_sweeps, &s_sweeps64);
+  const double* V = J.V[cur];
+  const double* S = J.S[cur];
+  for (int j = tid; j < np; j += nt) {
+    const bool pad = (np != n) && fabs(V[n * lds + j]) > 0.5;
+    s_w[j] = pad ? -1e300 : S[j * lds + j] * gscale;
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += nt) {
+    const double wi = s_w[i];
+    int r = 0;
+    for (int j = 0; j < np; ++j) {
+      const double wj = s_w[j];
+      r += (wj > wi) || (wj == wi && j < i);
+    }
+    s_rank[i] = r;
+    if (r < n) w_out[r] = wi;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * np; idx += nt) {
+    const int k = idx / np, i = idx - k * np;
+    const int r = s_rank[i];
+    if (r < n) V_out[(size_t)k * n + r] = V[k * lds + i];
+  }
+  if (tid == 0 && info) {
+    const int a = s_sweeps32 < 0 ? -s_sweeps32 : s_sweeps32, b = s_sweeps64 < 0 ? -s_sweeps64 : s_sweeps64;
+    info[0] = (s_sweeps32 < 0 || s_sweeps64 < 0) ? -(a + b) : (a + b);
+  }
+}
+
 inline bool jacobi2_ok(int n, bool single_precision) {
   return n >= 1 && n <= (single_precision ? JAC2_MAX_N_F32 : JAC2_MAX_N_F64);
 }
@@ -227,7 +340,17 @@ inline int jacobi2_eigh(const double* G, int n, int ldg, double* w, double* V, d
   static const bool disabled = getenv("TNB_NO_JACOBI2") != nullptr;  // A/B switch (profiling)
   if (disabled || !jacobi2_ok(n, single_precision)) return jacobi_eigh(G, n, ldg, w, V, scratch, info, st, single_precision, loose_tol);
   const int max_sweeps = 30;
-  static PerDeviceFlag attr_done[2];
+  static PerDeviceFlag attr_done[3];
+  static const bool no_mixed = getenv("TNB_NO_MIXED_JACOBI") != nullptr;  // A/B switch
+  if (!single_precision && !no_mixed && n <= JAC2_MIXED_MAX_N && n >= 8) {
+    const double tol = loose_tol > 0.0 ? loose_tol : 1e-14;
+    const size_t smem = jac2_smem_bytes<double>(n) + jac2_smem_bytes<float>(n);
+    TNB_CUDA(ensure_dyn_smem(attr_done[2], jacobi2_mixed_kernel,
+                             (int)(jac2_smem_bytes<double>(JAC2_MIXED_MAX_N) + jac2_smem_bytes<float>(JAC2_MIXED_MAX_N))));
+    jacobi2_mixed_kernel<<<1, jacobi2_threads(n), smem, st>>>(G, n, ldg, w, V, max_sweeps, tol, info);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+  }
   if (single_precision) {
     const float tol = loose_tol > 0.0 ? (float)loose_tol : 2e-6f;
     TNB_CUDA(ensure_dyn_smem(attr_done[0], jacobi2_eigh_kernel<float>, (int)jac2_smem_bytes<float>(JAC2_MAX_N_F32)));

@@ -250,8 +250,10 @@ class Tensor(object):
                     f = torch.einsum("ai,bi->abi", f, c)
                 else:
                     f = torch.einsum("ai,bi->ab", f, c)[..., None]
-            else:
+            elif c.requires_grad or f.requires_grad:  # differentiable path (cross_forward, tensor.py:1666-1680)
                 f = torch.einsum("ai,ibj->abj", f, c)
+            else:  # TT core: one library GEMM per core (tnb_matmul), no eager einsum
+                f = ops.matmul(f.contiguous(), c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
             f = f.reshape(-1, f.shape[-1])
         f = f.sum(dim=-1) if f.shape[-1] > 1 else f[..., 0]
         return f.reshape(list(self.shape))
