@@ -460,7 +460,9 @@ def run_ours(args):
     # ---- e2e: HOST buffers through the same batch entry point, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        EB = min(PB, 2)  # two tensors per step: 8 GiB of pinned host memory per rank is enough to be PCIe-bound
+        # two tensors per step on one GPU (8 GiB of pinned host memory is enough to be PCIe-bound); one per rank when several
+        # ranks share the host, so that N ranks pin N x 4 GiB, not N x 8 GiB
+        EB = min(PB, 2 if world == 1 else 1)
         hplan = ops.TTSVDBatchPlan(shape, torch.float32, EB, rmax=args.rank, device=dev, inflight=EB,
                                    use_tensorcore=not args.no_tc, host_io=True)
         hplan.ws = plan.ws  # share the workspace (EB <= PB slices)
@@ -494,8 +496,8 @@ def run_ours(args):
 
     cpu = None
     same_sample = None
-    if rank_id == 0 and not args.no_cpu_baseline:
-        # free the e2e / batch buffers first: the CPU leg needs host RAM and cores, not HBM
+    if rank_id == 0 and world == 1 and not args.no_cpu_baseline:  # N = 1 only (the other ranks would idle at the teardown)
+        # the e2e buffers are freed by now: the CPU leg needs host RAM and cores, not HBM
         cshape = tuple(int(s) for s in args.cpu_shape.split(","))
         arm = CpuArm(cshape, args.rank)
         arm.tune()

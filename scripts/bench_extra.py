@@ -25,6 +25,12 @@ if "cfg3" in which:  # tn.round_tt on random TT 128^10 rank 64 -> 16, fp64
     t2 = tnb.round_tt(t, rmax=16)
     coef = sum(c.numel() for c in cores)
     out["cfg3_round_tt_128^10_r64to16_f64"] = {"ms": ms, "Mcoef_per_s": coef / ms / 1e3, "ranks": t2.ranks_tt.tolist()}
+    # batch of 64 such tensors through ONE tnb_tt_round_batch call (8 in flight, one synchronisation)
+    B = 64
+    batch = [[torch.randn(c.shape, generator=g, device="cuda", dtype=torch.float64) for c in cores] for _ in range(B)]
+    msb = ev_ms(lambda: ops.tt_round_batch(batch, rmax=16), n=3)
+    out["cfg3_batch64"] = {"ms_total": msb, "ms_per_tensor": msb / B, "Mcoef_per_s": B * coef / msb / 1e3}
+    del batch
     print(json.dumps(out), flush=True)
 if "cfg4" in which:  # CP-ALS R=50 on a synthetic rank-50 256^4 (16 GiB fp32); a few sweeps timed, per-sweep reported
     shape = (256,) * 4
@@ -51,4 +57,16 @@ if "cfg5" in which:  # TT-cross 32^6, ranks 10, 3 sweeps (the unit of BASELINE c
                             return_info=True, suppress_warnings=True)
     torch.cuda.synchronize(); dt = (time.time() - t0) / nprob
     out["cfg5_cross_32^6_r10_3sweeps_f64"] = {"s_per_problem": dt, "evals_per_s": info["nsamples"] / dt, "val_eps": float(info["val_eps"])}
+    # B = 512 problems advanced together (tntorch_b200.cross_batch), three full sweeps (eps = 0)
+    def family(pid, *xs):
+        s = 1.0 + pid.double() / 512
+        for x in xs:
+            s = s + x
+        return 1.0 / s
+    tnb.cross_batch(family, dom, batch=8, batched_function=True, ranks_tt=10, max_iter=1, eps=0.0)
+    torch.cuda.synchronize(); t0 = time.time()
+    tb, infob = tnb.cross_batch(family, dom, batch=512, batched_function=True, ranks_tt=10, max_iter=3, eps=0.0, return_info=True)
+    torch.cuda.synchronize(); dtb = time.time() - t0
+    out["cfg5_cross_batch512"] = {"s_total": dtb, "problems_per_s": 512 / dtb, "evals_per_s": float(infob["nsamples"].sum()) / dtb,
+                                  "max_val_eps": float(infob["val_eps"].max())}
     print(json.dumps(out), flush=True)

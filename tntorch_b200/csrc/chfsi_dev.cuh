@@ -432,60 +432,97 @@ __global__ void cd_init_ctrl_kernel(ChfsiCtrl* ctrl) {
   }
 }
 
-// Enqueue the whole solve on `st`; returns without waiting.  G: n x n fp32 (TF32 filter products, fp32-exact
-// Rayleigh-Ritz product), d_trace: device scalar trace(G) (may be null), theta_out: b doubles, X_out: n x b doubles.
-// sweep_flags (device int, may be null): bit (1 << error) is OR-ed in when the chain fails, for the caller's final check.
-inline int eig_topk_chfsi_dev(const float* G, int n, int k, int b, const double* d_trace, double tol, CdWork<float>& w,
-                              double* theta_out, double* X_out, int* sweep_flags, cudaStream_t st) {
+// One solve, enqueued in pieces so that a batch can interleave the stages of several solves (sweep.cuh: the resident
+// filter kernels of all streams run one after the other, so tensor A's Rayleigh-Ritz step should be in flight while
+// tensor B's filter runs): cd_begin, cd_stage(0 .. CD_MAX_STAGES), cd_end.  G: n x n fp32 (TF32 filter products,
+// fp32-exact Rayleigh-Ritz product), d_trace: device scalar trace(G) (may be null), theta_out: b doubles, X_out: n x b
+// doubles.  sweep_flags (device int[4], may be null): bit (1 << error) is OR-ed into [0] when the chain fails.
+struct CdRun {
+  const float* G = nullptr;
+  int n = 0, k = 0, b = 0;
+  const double* d_trace = nullptr;
+  CdWork<float>* w = nullptr;
+  double *theta_out = nullptr, *X_out = nullptr;
+  int* sweep_flags = nullptr;
+  cudaStream_t st = 0;
+  CdRule rule;
+  CdRing<float> ring;
+  GemmPlan pl;
+  size_t chol_smem = 0, rot_smem = 0, rr_smem = 0;
+};
+
+inline int cd_begin(CdRun& r, const float* G, int n, int k, int b, const double* d_trace, double tol, CdWork<float>& w,
+                    double* theta_out, double* X_out, int* sweep_flags, cudaStream_t st) {
   typedef float TB;
   if (!chfsi_dev_ok(n, b) || b < k) return fail(TNB_ERR_UNSUPPORTED, "chfsi_dev: n=%d b=%d k=%d outside the envelope", n, b, k);
-  const int* skip = &w.ctrl->done;
-  CdRing<TB> ring;
-  for (int i = 0; i < 3; ++i) ring.p[i] = w.ring[i];
-  cd_init_ctrl_kernel<<<1, 32, 0, st>>>(w.ctrl);
-  TNB_LAUNCH_CHECK();
-  random_fill_kernel<TB><<<grid_for((int64_t)n * b), 256, 0, st>>>(w.ring[0], (int64_t)n * b, 0x1234567u);
-  TNB_LAUNCH_CHECK();
-  CdRule rule;
-  rule.k = k;
-  rule.mmax = 40;
-  rule.spread = 1e4;
-  rule.tol = tol;
-  rule.floor_tol = 1e-7;
-  rule.jac_tol = 1e-4;  // the Ritz basis only needs ~1e-4: the captured energy is second order in it, Q stays orthogonal
-  rule.last_stage = CD_MAX_STAGES;
-  const size_t chol_smem = (size_t)2 * b * (b | 1) * sizeof(double);
-  const size_t rot_smem = ((size_t)b * b + (size_t)32 * (b + 1)) * sizeof(TB);
-  const size_t rr_smem = jac2_smem_bytes<TB>(b) > (size_t)b * b * sizeof(double) ? jac2_smem_bytes<TB>(b) : (size_t)b * b * sizeof(double);
+  r.G = G; r.n = n; r.k = k; r.b = b; r.d_trace = d_trace; r.w = &w; r.theta_out = theta_out; r.X_out = X_out;
+  r.sweep_flags = sweep_flags; r.st = st;
+  for (int i = 0; i < 3; ++i) r.ring.p[i] = w.ring[i];
+  r.rule.k = k;
+  r.rule.mmax = 40;
+  r.rule.spread = 1e4;
+  r.rule.tol = tol;
+  r.rule.floor_tol = 1e-7;
+  r.rule.jac_tol = 1e-4;  // the Ritz basis only needs ~1e-4: the captured energy is second order in it, Q stays orthogonal
+  r.rule.last_stage = CD_MAX_STAGES;
+  r.chol_smem = (size_t)2 * b * (b | 1) * sizeof(double);
+  r.rot_smem = ((size_t)b * b + (size_t)32 * (b + 1)) * sizeof(TB);
+  r.rr_smem = jac2_smem_bytes<TB>(b) > (size_t)b * b * sizeof(double) ? jac2_smem_bytes<TB>(b) : (size_t)b * b * sizeof(double);
   static PerDeviceFlag attr_done[3];
   TNB_CUDA(ensure_dyn_smem(attr_done[0], cd_chol_kernel<TB>, 180 * 1024));
   TNB_CUDA(ensure_dyn_smem(attr_done[1], cd_rotate_kernel<TB>, 100 * 1024));
   TNB_CUDA(ensure_dyn_smem(attr_done[2], cd_rr_kernel<TB>, (int)jac2_smem_bytes<TB>(JAC2_MAX_N_F32)));
-  GemmPlan pl = plan_gemm(n, b, n, false);
-  for (int stage = 0; stage <= CD_MAX_STAGES; ++stage) {
-    if (stage >= 1) {
-      float* fb[3] = {w.ring[0], w.ring[1], w.ring[2]};
-      TNB_TRY(cheb_filter_f32(G, n, b, fb, 1, nullptr, nullptr, nullptr, w.fws, w.fws_bytes, st, w.ctrl, stage));
-    }
-    // the block to orthonormalise is ring[0] (random start at stage 0, the filter's result afterwards)
-    cd_gram_partial_kernel<TB><<<w.P, 256, 0, st>>>(w.ring[0], w.ring[0], n, b, w.gpart, skip, stage);
-    TNB_LAUNCH_CHECK();
-    cd_chol_kernel<TB><<<1, 1024, chol_smem, st>>>(w.gpart, w.P, b, w.Sg, w.cscr, w.T1, w.ctrl, stage, 1);
-    TNB_LAUNCH_CHECK();
-    cd_rotate_kernel<TB><<<(n + 31) / 32, 256, rot_smem, st>>>(w.ring[0], w.T1, w.Xo, ring, n, b, w.ctrl, stage, 0);
-    TNB_LAUNCH_CHECK();
-    TNB_TRY((gemm_splitk<TB, TB, TB, TB, TB>(pl, n, b, n, G, n, false, w.Xo, b, false, reinterpret_cast<TB*>(w.partial), w.Wb, b,
-                                             (TB)1, nullptr, 0, (TB)0, nullptr, 0, (TB)0, false, (TB*)nullptr, 0, st, skip, stage)));
-    cd_gram_partial_kernel<TB><<<w.P, 256, 0, st>>>(w.Xo, w.Wb, n, b, w.gpart, skip, stage);
-    TNB_LAUNCH_CHECK();
-    cd_rr_kernel<TB><<<1, 1024, rr_smem, st>>>(w.gpart, w.P, b, w.Sg, w.Qd, w.T2, w.lam, d_trace, w.ctrl, stage, rule);
-    TNB_LAUNCH_CHECK();
-    cd_rotate_kernel<TB><<<(n + 31) / 32, 256, rot_smem, st>>>(w.Xo, w.T2, nullptr, ring, n, b, w.ctrl, stage, 1);
-    TNB_LAUNCH_CHECK();
-  }
-  cd_finish_kernel<TB><<<grid_for((int64_t)n * b), 256, 0, st>>>(w.ring[0], w.lam, n, b, theta_out, X_out, w.ctrl, sweep_flags);
+  r.pl = plan_gemm(n, b, n, false);
+  cd_init_ctrl_kernel<<<1, 32, 0, st>>>(w.ctrl);
+  TNB_LAUNCH_CHECK();
+  random_fill_kernel<TB><<<grid_for((int64_t)n * b), 256, 0, st>>>(w.ring[0], (int64_t)n * b, 0x1234567u);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
+}
+
+inline int cd_stage(CdRun& r, int stage) {
+  typedef float TB;
+  CdWork<float>& w = *r.w;
+  const int n = r.n, b = r.b;
+  cudaStream_t st = r.st;
+  const int* skip = &w.ctrl->done;
+  if (stage >= 1) {
+    float* fb[3] = {w.ring[0], w.ring[1], w.ring[2]};
+    TNB_TRY(cheb_filter_f32(r.G, n, b, fb, 1, nullptr, nullptr, nullptr, w.fws, w.fws_bytes, st, w.ctrl, stage));
+  }
+  // the block to orthonormalise is ring[0] (random start at stage 0, the filter's result afterwards)
+  cd_gram_partial_kernel<TB><<<w.P, 256, 0, st>>>(w.ring[0], w.ring[0], n, b, w.gpart, skip, stage);
+  TNB_LAUNCH_CHECK();
+  cd_chol_kernel<TB><<<1, 1024, r.chol_smem, st>>>(w.gpart, w.P, b, w.Sg, w.cscr, w.T1, w.ctrl, stage, 1);
+  TNB_LAUNCH_CHECK();
+  cd_rotate_kernel<TB><<<(n + 31) / 32, 256, r.rot_smem, st>>>(w.ring[0], w.T1, w.Xo, r.ring, n, b, w.ctrl, stage, 0);
+  TNB_LAUNCH_CHECK();
+  TNB_TRY((gemm_splitk<TB, TB, TB, TB, TB>(r.pl, n, b, n, r.G, n, false, w.Xo, b, false, reinterpret_cast<TB*>(w.partial), w.Wb, b,
+                                           (TB)1, nullptr, 0, (TB)0, nullptr, 0, (TB)0, false, (TB*)nullptr, 0, st, skip, stage)));
+  cd_gram_partial_kernel<TB><<<w.P, 256, 0, st>>>(w.Xo, w.Wb, n, b, w.gpart, skip, stage);
+  TNB_LAUNCH_CHECK();
+  cd_rr_kernel<TB><<<1, 1024, r.rr_smem, st>>>(w.gpart, w.P, b, w.Sg, w.Qd, w.T2, w.lam, r.d_trace, w.ctrl, stage, r.rule);
+  TNB_LAUNCH_CHECK();
+  cd_rotate_kernel<TB><<<(n + 31) / 32, 256, r.rot_smem, st>>>(w.Xo, w.T2, nullptr, r.ring, n, b, w.ctrl, stage, 1);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+inline int cd_end(CdRun& r) {
+  CdWork<float>& w = *r.w;
+  cd_finish_kernel<float><<<grid_for((int64_t)r.n * r.b), 256, 0, r.st>>>(w.ring[0], w.lam, r.n, r.b, r.theta_out, r.X_out, w.ctrl,
+                                                                           r.sweep_flags);
+  TNB_LAUNCH_CHECK();
+  return TNB_OK;
+}
+
+// The whole solve on one stream; returns without waiting.
+inline int eig_topk_chfsi_dev(const float* G, int n, int k, int b, const double* d_trace, double tol, CdWork<float>& w,
+                              double* theta_out, double* X_out, int* sweep_flags, cudaStream_t st) {
+  CdRun r;
+  TNB_TRY(cd_begin(r, G, n, k, b, d_trace, tol, w, theta_out, X_out, sweep_flags, st));
+  for (int stage = 0; stage <= CD_MAX_STAGES; ++stage) TNB_TRY(cd_stage(r, stage));
+  return cd_end(r);
 }
 
 }  // namespace tnb

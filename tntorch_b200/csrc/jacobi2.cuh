@@ -248,6 +248,28 @@ __global__ void __launch_bounds__(1024) jacobi2_mixed_kernel(const double* __res
   __syncthreads();
   const int c32 = jac2_solve(F, max_sweeps, &s_sweeps32);
   const float* V32 = F.V[c32];
+  {
+    // ~500 fp32 rotations per column leave V32 orthogonal to ~1e-5: a first Newton-Schulz step in fp32 (cheap) brings
+    // that to ~1e-7, the fp64 step below then to ~1e-14 (one fp64 step from 1e-5 would only reach ~1e-10 and the
+    // eigenvalues of the congruence V^T G V would be off by as much)
+    float* E32 = F.S[0];
+    float* Vn32 = F.V[c32 ^ 1];
+    for (int idx = tid; idx < np * np; idx += nt) {
+      const int i = idx / np, j = idx - i * np;
+      float acc = 0.f;
+      for (int c = 0; c < np; ++c) acc = fmaf(V32[c * lds + i], V32[c * lds + j], acc);
+      E32[i * lds + j] = (i == j ? 1.5f : 0.f) - 0.5f * acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < np * np; idx += nt) {
+      const int i = idx / np, j = idx - i * np;
+      float acc = 0.f;
+      for (int c = 0; c < np; ++c) acc = fmaf(V32[i * lds + c], E32[c * lds + j], acc);
+      Vn32[i * lds + j] = acc;
+    }
+    __syncthreads();
+    V32 = Vn32;
+  }
   // ---- promote, re-orthonormalise (fp64 Newton-Schulz), congruence ----
   double* Vp = J.V[1];   // promoted basis
   double* E = J.S[0];    // 1.5 I - 0.5 V^T V (full storage), later overwritten by S2

@@ -310,6 +310,8 @@ inline int tt_round_spec_enqueue(ArenaT& ar, bool dry, const T* const* cores_in,
     if (!dry) {
       if (!ar.ok) return fail(TNB_ERR_WORKSPACE, "tt_round: workspace too small (need > %zu bytes)", ar.off);
       TNB_TRY(spec_step_gram<T>(cx, M, rows, n, t == 0, step, false));
+      TNB_TRY(spec_step_eig_begin<T>(cx, step));
+      for (int stage = 0; stage <= CD_MAX_STAGES; ++stage) TNB_TRY(spec_step_eig_stage<T>(step, stage));
       TNB_TRY(spec_step_rest<T>(cx, M, rows, n, rmax[mu - 1], cores_out + d.slot[mu], left, mu, step, false));
       const int64_t rank = d.rcap[mu];
       const int64_t rowsP = d.ra[mu - 1] * d.shape[mu - 1];

@@ -428,6 +428,7 @@ struct SpecStep {
   int ldv = 0, b = 0, used_tc = 0;
   bool chfsi = false, tc_gram = false;
   int64_t L = 0, kcap = 0;
+  CdRun cd;  // the subspace solve of this step, enqueued stage by stage
 };
 
 template <typename T, class ArenaT>
@@ -484,7 +485,32 @@ inline int spec_step_gram(const StepCtx& cx, const T* C, int64_t rows, int64_t n
   return TNB_OK;
 }
 
-// phase 2: eigenpairs, rank rule + speculation check, factor extraction, projection
+// phase 2a: start the eigen stage — a small Gram matrix is solved right here (one Jacobi kernel), a large one begins its
+// subspace solve, whose stages are enqueued one at a time by spec_step_eig_stage so that a batch can interleave them
+template <typename T>
+inline int spec_step_eig_begin(const StepCtx& cx, SpecStep<T>& s) {
+  const int64_t L = s.L;
+  cudaStream_t st = cx.st;
+  if (!s.chfsi) {
+    // a TF32 Gram is accurate to ~2e-6 ||G||: rotating it in fp32 (backward error ~1e-6 ||G||, covered by the accept rule's
+    // noise allowance) is consistent with it and 3-4x cheaper than fp64 on this machine (~16 fp64 FMAs / clk / SM);
+    // eigenvalues still come out as fp64 Rayleigh quotients and the vectors are re-orthonormalised (jacobi2.cuh).
+    // The same holds for fp32 DATA whatever Gram kernel produced G, as long as the accept rule — which then guards the
+    // fp32 solve instead of the TF32 Gram, same noise allowance — finds the spectrum benign; a rejected step is repeated
+    // on the host-driven path with fp64 rotations.
+    const bool single = std::is_same<T, float>::value && (cx.allow_tc && !cx.exact_gram) && jacobi2_ok((int)L, true);
+    s.used_tc = (s.used_tc || single) ? 1 : 0;
+    return jacobi2_eigh(s.G, (int)L, (int)L, s.w, s.V, s.jscratch, s.jinfo, st, single, single ? 2e-6 : 0.0);
+  }
+  if (cx.info) cx.info->eig_solves += 1;
+  return cd_begin(s.cd, s.Gf, (int)L, (int)s.kcap, s.b, &cx.sc->trace, 1e-6, s.cw, s.w, s.V, cx.d_flags, st);
+}
+template <typename T>
+inline int spec_step_eig_stage(SpecStep<T>& s, int stage) {
+  return s.chfsi ? cd_stage(s.cd, stage) : TNB_OK;
+}
+
+// phase 2b: end of the eigen stage, rank rule + speculation check, factor extraction, projection
 template <typename T>
 inline int spec_step_rest(const StepCtx& cx, const T* C, int64_t rows, int64_t n, int32_t rm, T* core, T* Cn, int mu,
                           SpecStep<T>& s, bool prof_on) {
@@ -495,19 +521,10 @@ inline int spec_step_rest(const StepCtx& cx, const T* C, int64_t rows, int64_t n
   Prof& prof = Prof::get();
   const bool concurrent = (cx.flags & TNB_FLAG_CONCURRENT) != 0;
   if (!s.chfsi) {
-    // a TF32 Gram is accurate to ~2e-6 ||G||: rotating it in fp32 (backward error ~1e-6 ||G||, covered by the accept rule's
-    // noise allowance) is consistent with it and 3-4x cheaper than fp64 on this machine (~16 fp64 FMAs / clk / SM);
-    // eigenvalues still come out as fp64 Rayleigh quotients and the vectors are re-orthonormalised (jacobi2.cuh)
-    // The same holds for fp32 DATA whatever Gram kernel produced G, as long as the accept rule — which then guards the
-    // fp32 solve instead of the TF32 Gram, same noise allowance — finds the spectrum benign; a rejected step is repeated
-    // on the host-driven path with fp64 rotations.
-    const bool single = std::is_same<T, float>::value && (cx.allow_tc && !cx.exact_gram) && jacobi2_ok((int)L, true);
-    TNB_TRY(jacobi2_eigh(s.G, (int)L, (int)L, s.w, s.V, s.jscratch, s.jinfo, st, single, single ? 2e-6 : 0.0));
-    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)L, rm, 0, batch_mode, cx.sc, (s.used_tc || single) ? 1 : 0, (int)L);
+    rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)L, rm, 0, batch_mode, cx.sc, s.used_tc, (int)L);
   } else {
-    TNB_TRY(eig_topk_chfsi_dev(s.Gf, (int)L, (int)s.kcap, s.b, &cx.sc->trace, 1e-6, s.cw, s.w, s.V, cx.d_flags, st));
+    TNB_TRY(cd_end(s.cd));
     rank_rule_kernel<<<1, 32, 0, st>>>(s.w, (int)L, (int)s.kcap, rm, 1, batch_mode, cx.sc, s.used_tc, s.b);
-    if (cx.info) cx.info->eig_solves += 1;
   }
   TNB_LAUNCH_CHECK();
   spec_check_kernel<<<1, 32, 0, st>>>(cx.sc, (int)s.kcap, cx.d_ranks + mu, cx.d_flags);
@@ -702,7 +719,15 @@ inline int spec_phase1(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, int 
   return spec_step_gram<T>(r.cx, r.C, d.rows[mu], d.shape[mu] * d.rcap[mu + 1], t == 0, r.step, prof_on);
 }
 template <typename T, class ArenaT>
-inline int spec_phase2(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, const int32_t* rmax, int mu, int t, bool prof_on) {
+inline int spec_phase2a(SpecRun<T, ArenaT>& r, bool dry) {
+  return dry ? TNB_OK : spec_step_eig_begin<T>(r.cx, r.step);
+}
+template <typename T, class ArenaT>
+inline int spec_phase2s(SpecRun<T, ArenaT>& r, bool dry, int stage) {
+  return dry ? TNB_OK : spec_step_eig_stage<T>(r.step, stage);
+}
+template <typename T, class ArenaT>
+inline int spec_phase2b(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, const int32_t* rmax, int mu, int t, bool prof_on) {
   ArenaT& ar = *r.ar;
   if (!dry) {
     TNB_TRY(spec_step_rest<T>(r.cx, r.C, d.rows[mu], d.shape[mu] * d.rcap[mu + 1], rmax[mu - 1], r.cores + d.slot[mu],
@@ -711,6 +736,13 @@ inline int spec_phase2(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, cons
   }
   ar.off = r.mark;
   return TNB_OK;
+}
+// the whole phase 2 of one tensor
+template <typename T, class ArenaT>
+inline int spec_phase2(SpecRun<T, ArenaT>& r, bool dry, const SweepDims& d, const int32_t* rmax, int mu, int t, bool prof_on) {
+  TNB_TRY((spec_phase2a<T, ArenaT>(r, dry)));
+  for (int stage = 0; stage <= CD_MAX_STAGES; ++stage) TNB_TRY((spec_phase2s<T, ArenaT>(r, dry, stage)));
+  return spec_phase2b<T, ArenaT>(r, dry, d, rmax, mu, t, prof_on);
 }
 template <typename T, class ArenaT>
 inline int spec_end(SpecRun<T, ArenaT>& r, const SweepDims& d) {
@@ -897,19 +929,18 @@ inline int ttsvd_batch_impl(void* workspace, size_t per_tensor_bytes, int inflig
     for (int s = 0; s < g && rc == TNB_OK; ++s)
       rc = spec_begin<T, Arena>(runs[s], arenas[s], false, data[g0 + s], d, eps, bflags, cores[g0 + s], &infos[g0 + s],
                                 pool.st[s], hbs + g0 + s);
-    // Enqueue order.  "wave" (default): a diagonal wavefront — in wave w tensor s is at step w - s, so at any moment the
-    // in-flight tensors are at DIFFERENT steps and the whole-GPU kernels of some run beside the eigen chains of others
-    // (the resident filter kernels of all streams are chained one after the other, cheb_filter.cuh, so tensors at the
-    // same step would queue their eigen chains behind each other).  "phase": step by step, all Gram kernels of a step
-    // first, then every tensor's eigen chain + projection.
-    static const bool phase_major = getenv("TNB_BATCH_ORDER") && !strcmp(getenv("TNB_BATCH_ORDER"), "phase");
+    // Enqueue order (TNB_BATCH_ORDER, measured on B200 with 6 x 64^5 in flight — profiles/r02_batch_schedule.md):
+    //   "stage" (default): step by step; all Gram kernels of a step, then the eigen stages of all tensors INTERLEAVED
+    //            stage by stage (the resident filter kernels of all streams run one after the other, cheb_filter.cuh:
+    //            this way tensor A's Rayleigh-Ritz step is in flight while tensor B's filter runs), then every
+    //            tensor's rank rule + projection;
+    //   "phase": step by step, each tensor's whole eigen chain enqueued at once (chains then queue behind each other);
+    //   "wave":  a diagonal wavefront — in wave w tensor s is at step w - s.
+    static const char* order_env = getenv("TNB_BATCH_ORDER");
+    const bool order_phase = order_env && !strcmp(order_env, "phase");
+    const bool order_wave = order_env && !strcmp(order_env, "wave");
     const int steps = N - 1;
-    if (phase_major) {
-      for (int mu = N - 1, t = 0; mu >= 1 && rc == TNB_OK; --mu, ++t) {
-        for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase1<T, Arena>(runs[s], false, d, mu, t, false);
-        for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, mu, t, false);
-      }
-    } else {
+    if (order_wave) {
       for (int w = 0; w < steps + g - 1 && rc == TNB_OK; ++w) {
         for (int s = 0; s < g && rc == TNB_OK; ++s) {
           const int t = w - s;
@@ -918,6 +949,18 @@ inline int ttsvd_batch_impl(void* workspace, size_t per_tensor_bytes, int inflig
         for (int s = 0; s < g && rc == TNB_OK; ++s) {
           const int t = w - s;
           if (t >= 0 && t < steps) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, N - 1 - t, t, false);
+        }
+      }
+    } else {
+      for (int mu = N - 1, t = 0; mu >= 1 && rc == TNB_OK; --mu, ++t) {
+        for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase1<T, Arena>(runs[s], false, d, mu, t, false);
+        if (order_phase) {
+          for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2<T, Arena>(runs[s], false, d, rmax, mu, t, false);
+        } else {
+          for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2a<T, Arena>(runs[s], false);
+          for (int stage = 0; stage <= CD_MAX_STAGES && rc == TNB_OK; ++stage)
+            for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2s<T, Arena>(runs[s], false, stage);
+          for (int s = 0; s < g && rc == TNB_OK; ++s) rc = spec_phase2b<T, Arena>(runs[s], false, d, rmax, mu, t, false);
         }
       }
     }
