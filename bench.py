@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--no-tc", action="store_true", help="generic CUDA-core kernels only (A/B runs)")
     ap.add_argument("--cpu-shape", default="32,32,32,32,32", help="bounded sample timed on the host cores")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left free by the persistent kernels (measured: no gain on B200, default 0)")
-    ap.add_argument("--per-gpu-batch", type=int, default=6,
+    ap.add_argument("--per-gpu-batch", type=int, default=8,
                     help="independent tensors per GPU and step, decomposed by ONE tnb_ttsvd_batch call (the library keeps "
                          "them in flight on internal streams: the latency-bound eigen chains of one tensor run beside the "
                          "bandwidth-bound Gram/projection kernels of another)")

@@ -95,9 +95,9 @@ int tnb_ttsvd(int dtype, const void* data, int ndim, const int64_t* shape, const
  *   data[i] / cores[i]  device pointers of tensor i and of its cores buffer (cores_capacity elements each, layout as
  *                       in tnb_ttsvd); ranks_host: batch * (ndim + 1) ints
  *   workspace           k * per_tensor_bytes with k >= 1: up to min(k, 8) decompositions are in flight at once on
- *                       internal streams, enqueued from the calling thread phase by phase (all Gram kernels of a step,
- *                       then every tensor's eigen chain + projection) and synchronised ONCE; `stream` is forked from
- *                       and joined to.  tnb_ttsvd_batch_workspace_bytes() returns the recommended size (6 in flight)
+ *                       internal streams, enqueued from the calling thread step by step (all Gram kernels of a step,
+ *                       then the eigen stages of all tensors interleaved, then every projection) and synchronised ONCE; `stream` is forked from
+ *                       and joined to.  tnb_ttsvd_batch_workspace_bytes() returns the recommended size (8 in flight)
  *                       and, through per_tensor_bytes, the unit.
  *   norms_host          optional, batch doubles: ||T_i||_F
  *   speculative_host    optional, batch ints: 1 if tensor i was accepted from the single-synchronisation sweep

@@ -179,7 +179,7 @@ class TTSVDBatchPlan:
     (tn.Tensor(X[B, ...], ranks_tt=r, batch=True); bench.py; dist.ttsvd_batch_sharded).  Up to `inflight` tensors are
     in flight at once inside the library (internal streams, one enqueueing thread, one synchronisation)."""
 
-    def __init__(self, shape: Sequence[int], dtype: torch.dtype, batch: int, rmax=None, device="cuda", inflight: int = 6,
+    def __init__(self, shape: Sequence[int], dtype: torch.dtype, batch: int, rmax=None, device="cuda", inflight: int = 8,
                  use_tensorcore: bool = True, batch_mode: bool = False, host_io: bool = False):
         self.shape = [int(s) for s in shape]
         self.N = len(self.shape)
@@ -250,7 +250,7 @@ class TTSVDBatchPlan:
         return out
 
 
-def ttsvd_batch(tensors, rmax=None, eps: float = 1e-14, batch_mode: bool = False, inflight: int = 6,
+def ttsvd_batch(tensors, rmax=None, eps: float = 1e-14, batch_mode: bool = False, inflight: int = 8,
                 use_tensorcore: bool = True, return_info: bool = False):
     """Decompose a batch of dense tensors of one shape (a [B, ...] tensor or a sequence): tn.Tensor(..., batch=True)
     and every caller that decomposes many tensors.  Returns a list (per tensor) of lists of cores (fresh tensors)."""
