@@ -340,16 +340,25 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 // Sum the split-K partial tiles in fp64 (fixed order), mirror to the lower triangle.
 __global__ void gram_tc_finalize_kernel(const GramTcParams p, double* __restrict__ G, float* __restrict__ Gf) {
   if (p.fold > 1) {  // single 128 x 128 tile; fold the diagonal n_orig x n_orig blocks
+    // one WARP per output element: the ksplit * fold terms (hundreds, strided) are dealt to the lanes and combined by a
+    // shuffle tree in a fixed order — deterministic like the serial sum, without its 300-deep dependent chain per thread
     const int no = p.n_orig;
     const size_t split_stride = (size_t)p.num_tiles * 128 * p.tn;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < no * no; idx += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int nterms = p.ksplit * p.fold;
+    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < no * no; idx += warps) {
       const int i = idx / no, j = idx % no;
       double s = 0.0;
-      for (int z = 0; z < p.ksplit; ++z)
-        for (int a = 0; a < p.fold; ++a)
-          s += (double)p.partial[(size_t)z * split_stride + (size_t)(a * no + i) * p.tn + (a * no + j)];
-      G[idx] = s;
-      if (Gf) Gf[idx] = (float)s;
+      for (int t = lane; t < nterms; t += 32) {
+        const int z = t / p.fold, a = t - z * p.fold;
+        s += (double)p.partial[(size_t)z * split_stride + (size_t)(a * no + i) * p.tn + (a * no + j)];
+      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        G[idx] = s;
+        if (Gf) Gf[idx] = (float)s;
+      }
     }
     return;
   }
@@ -495,7 +504,7 @@ inline int gram_tc_f32(const float* A, int64_t rows, int64_t n, double* G, float
   dim3 grid((unsigned)p.num_tiles, (unsigned)p.ksplit);
   gram_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, tmap, p);
   TNB_LAUNCH_CHECK();
-  const int64_t total = n_in * n_in;
+  const int64_t total = n_in * n_in * (p.fold > 1 ? 32 : 1);  // folded form: one warp per element
   gram_tc_finalize_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(p, G, Gf);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
