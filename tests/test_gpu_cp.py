@@ -81,4 +81,4 @@ def test_cp_on_tucker_core():
     out = ops.cp_als(X, 3, max_iter=0, init=init)
     assert all(torch.equal(a, b) for a, b in zip(out, init))
     out, info = ops.cp_als(X, 3, max_iter=3, tol=float("-inf"), init=init, return_info=True)
-    assert info["errors"][-1] < 1e-10  # started at the exact factors: stays there
+    assert info["errors"][-1] < 1e-6  # started at the exact factors: stays there (the Gram-form error estimate resolves ~1e-8)
