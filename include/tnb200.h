@@ -111,8 +111,10 @@ int tnb_ttsvd_batch(int dtype, const void* const* data, int batch, int ndim, con
                     int64_t cores_capacity, int32_t* ranks_host, double* norms_host, int32_t* speculative_host,
                     void* stream);
 
-/* Same, but `data_host` / `cores_host` are HOST buffers (pinned for full speed): the H2D copy is
- * chunked and overlapped with the first Gram pass, cores are copied back before returning.
+/* Same as tnb_ttsvd, but `data_host` / `cores_host` are HOST buffers (pinned for full speed): the tensor is copied to
+ * `device_buffer` in 256 MiB chunks on `stream` (so that a pageable source still overlaps its staging with the DMA), the
+ * decomposition runs on the same stream AFTER the copy (nothing of it overlaps the transfer: at 4 GiB per tensor the call
+ * is bound by the PCIe link either way), and the cores are copied back before returning.
  * `device_buffer` must hold the dense tensor (prod(shape) elements) and is left filled. */
 int tnb_ttsvd_host(int dtype, const void* data_host, int ndim, const int64_t* shape, const int32_t* rmax, double eps,
                    uint32_t flags, void* device_buffer, void* workspace, size_t workspace_bytes, void* cores_dev,

@@ -39,3 +39,14 @@ def test_tucker_rounding_matches_reference(name):
     for U in t.Us:  # factors are orthonormal (left_ortho=True split)
         if U is not None:
             assert (U.T @ U - torch.eye(U.shape[1], device="cuda", dtype=U.dtype)).abs().max().item() < 1e-8
+
+
+def test_eps_constructor_on_one_mode_data():
+    """Tensor(data, eps=...) on 1-D / 0-D data used to raise (the error kernel needs two modes)."""
+    import tntorch_b200 as tnb
+
+    v = torch.arange(7, dtype=torch.float64).cuda()
+    t = tnb.Tensor(v, eps=1e-3)
+    assert list(t.shape) == [7] and float((t.torch() - v).abs().max()) < 1e-2 * float(v.abs().max())
+    s = tnb.Tensor(torch.tensor(3.5).cuda(), eps=1e-3)
+    assert abs(float(s.torch().reshape(-1)[0]) - 3.5) < 1e-2

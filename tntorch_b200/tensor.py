@@ -105,7 +105,8 @@ class Tensor(object):
                 # error against the dense data, measured by the device reconstruct-and-diff kernel.
                 self.cores = ops.ttsvd(data, rmax=None, eps=eps)
                 self.Us = [None] * N
-                reached = float(ops.tt_relative_error(data, self.cores))
+                # a 1-mode "tensor" is stored exactly by its single core: nothing to measure (and the error kernel needs N >= 2)
+                reached = float(ops.tt_relative_error(data, self.cores)) if N >= 2 else 0.0
                 if reached < eps:
                     self.round_tucker((1 + eps) / (1 + reached) - 1, algorithm=algorithm)
                 Us = self.Us
