@@ -304,3 +304,39 @@ def cross_family_function(b, family=512):
         return 1.0 / s
 
     return f
+
+
+# ---- callers that re-round in loops: hadamard_sum, shift_mode, TTMatrix
+HADAMARD_SUM_CASES = {
+    "hs_3x_6545_r3": dict(shape=(6, 5, 4, 5), ranks=[(1, 3, 3, 3, 1), (1, 2, 4, 2, 1), (1, 3, 2, 3, 1)], seed=170),
+    "hs_2x_8888_r5": dict(shape=(8, 8, 8, 8), ranks=[(1, 5, 5, 5, 1), (1, 4, 4, 4, 1)], seed=171),
+    "hs_4x_444_r2": dict(shape=(4, 4, 4), ranks=[(1, 2, 2, 1)] * 4, seed=172),
+}
+SHIFT_MODE_CASES = {
+    # (TT spec, mode, shift, eps)
+    "shift_right2": (dict(shape=(4, 5, 6, 7), ranks=(1, 3, 4, 3, 1), seed=175), 0, 2, 1e-6),
+    "shift_left3": (dict(shape=(4, 5, 6, 7), ranks=(1, 3, 4, 3, 1), seed=176), 3, -3, 1e-6),
+    "shift_same": (dict(shape=(6, 6, 6, 6, 6), ranks=(1, 4, 4, 4, 4, 1), seed=177), 1, 2, "same"),
+}
+TTMATRIX_CASES = {
+    # (matrix seed, input dims, output dims, ranks, batch)
+    "ttm_16x24": dict(seed=180, input_dims=[4, 4], output_dims=[4, 6], ranks=[5], batch=0),
+    "ttm_64x64_3": dict(seed=181, input_dims=[4, 4, 4], output_dims=[4, 4, 4], ranks=[6, 6], batch=0),
+    "ttm_batch3_36x20": dict(seed=182, input_dims=[6, 6], output_dims=[4, 5], ranks=[7], batch=3),
+}
+
+
+def shift_mode_input(spec):
+    return random_tt(spec["shape"], list(spec["ranks"][1:-1]), spec["seed"])
+
+
+def hadamard_operands(spec):
+    return [random_tt(spec["shape"], list(r[1:-1]), spec["seed"] + 13 * k) for k, r in enumerate(spec["ranks"])]
+
+
+def ttmatrix_input(spec):
+    import math
+
+    rows, cols = math.prod(spec["input_dims"]), math.prod(spec["output_dims"])
+    shape = ([spec["batch"]] if spec["batch"] else []) + [rows, cols]
+    return _rng(spec["seed"]).standard_normal(shape)

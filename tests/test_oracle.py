@@ -114,3 +114,60 @@ def test_rect_maxvol_oracle_matches_reference(name):
     idx, C = orc.py_rect_maxvol(cases.make_matrix(spec), **kw)
     assert list(idx) == list(g[f"{name}/index"])
     np.testing.assert_allclose(C, g[f"{name}/C"], atol=1e-12)
+
+
+# ---- §8(f)-3 callers: the reference's outputs (callers.npz) against the oracle's own primitives
+@pytest.mark.parametrize("name", list(cases.HADAMARD_SUM_CASES))
+def test_hadamard_sum_golden_is_the_dense_sum(name):
+    """metrics.hadamard_sum: the reference's exact and re-rounded values against the dense elementwise product."""
+    g = _g("callers.npz")
+    ops64 = cases.hadamard_operands(cases.HADAMARD_SUM_CASES[name])
+    dense = np.prod(np.stack([orc.tt_reconstruct(c) for c in ops64]), axis=0).sum()
+    assert abs(float(g[f"{name}/exact"]) - dense) <= 1e-12 * abs(dense)
+    assert abs(float(g[f"{name}/svd"]) - dense) <= 1e-6 * abs(dense)
+
+
+@pytest.mark.parametrize("name", list(cases.SHIFT_MODE_CASES))
+def test_shift_mode_golden(name):
+    """tools.shift_mode (tools.py:650-697) restated on the oracle's orthogonalisation + truncated_svd."""
+    g = _g("callers.npz")
+    spec, n, shift, eps = cases.SHIFT_MODE_CASES[name]
+    cores = [c.copy() for c in cases.shift_mode_input(spec)]
+    # orthogonalize(n)
+    for mu in range(n):
+        orc.left_orthogonalize(cores, mu)
+    for mu in range(len(cores) - 1, n, -1):
+        orc.right_orthogonalize(cores, mu)
+    sign = 1 if shift > 0 else -1
+    for i in range(n, n + shift, sign):
+        c1, c2, lo = (i, i + 1, True) if sign == 1 else (i - 1, i, False)
+        R1, I1, R2 = cores[c1].shape
+        _, I2, R3 = cores[c2].shape
+        sc = np.einsum("iaj,jbk->ibak", cores[c1], cores[c2]).reshape(R1 * I2, I1 * R3)
+        kw = dict(eps=0, rmax=R2) if eps == "same" else dict(eps=eps / np.sqrt(abs(shift)))
+        left, right = orc.truncated_svd(sc, left_ortho=lo, **kw)
+        cores[c1], cores[c2] = left.reshape(R1, I2, -1), right.reshape(-1, I1, R3)
+    got = orc.tt_reconstruct(cores)
+    ref = g[f"{name}/full"]
+    assert got.shape == ref.shape
+    assert [1] + [c.shape[2] for c in cores] == g[f"{name}/ranks"].tolist()
+    assert np.linalg.norm(got - ref) <= 1e-9 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("name", list(cases.TTMATRIX_CASES))
+def test_ttmatrix_golden(name):
+    """TTMatrix.__init__ (matrix.py:96): permute to (i_k o_k) modes, then the oracle's TT-SVD with the rank caps."""
+    g = _g("callers.npz")
+    spec = cases.TTMATRIX_CASES[name]
+    M = cases.ttmatrix_input(spec)
+    idims, odims, d = spec["input_dims"], spec["output_dims"], len(spec["input_dims"])
+    samples = M if spec["batch"] else M[None]
+    outs = []
+    for S in samples:
+        X = S.reshape(idims + odims).transpose([k + s * d for k in range(d) for s in (0, 1)])
+        X = X.reshape([idims[k] * odims[k] for k in range(d)])
+        full = orc.tt_reconstruct(orc.tt_svd(X, ranks_tt=spec["ranks"]))
+        full = full.reshape([s for k in range(d) for s in (idims[k], odims[k])])
+        outs.append(full.transpose([2 * k for k in range(d)] + [2 * k + 1 for k in range(d)]).reshape(S.shape))
+    got = np.stack(outs) if spec["batch"] else outs[0]
+    np.testing.assert_allclose(got, g[f"{name}/full"], atol=1e-9 * np.abs(M).max())
