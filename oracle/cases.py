@@ -176,6 +176,9 @@ MAXVOL_CASES = {
 CP_CASES = {
     "cp_16x4_R5": dict(shape=(16,) * 4, Rtrue=5, R=5, sweeps=10, noise=1e-2, seed=50, dtype="float64"),
     "cp_20x3_R8": dict(shape=(20, 18, 16), Rtrue=8, R=8, sweeps=8, noise=1e-3, seed=51, dtype="float64"),
+    # five modes (every branch of the dimension-tree sweep: chain, inner modes, transposed last mode) and two modes
+    "cp_5mode_R4": dict(shape=(8, 7, 6, 5, 9), Rtrue=4, R=4, sweeps=8, noise=1e-2, seed=52, dtype="float64"),
+    "cp_2mode_R3": dict(shape=(30, 20), Rtrue=3, R=3, sweeps=4, noise=1e-2, seed=53, dtype="float64"),
 }
 
 # ---- TT-cross (seeded global NumPy/torch RNGs; function f(x) = 1 / (shift + sum_i x_i)) ----------------

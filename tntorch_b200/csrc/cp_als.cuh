@@ -25,9 +25,21 @@ __global__ void khatri_reduce_kernel(const T* __restrict__ Y, const T* __restric
     const int r = (int)(idx % R);
     const int64_t q = (idx / R) % Q, l = idx / (R * Q);
     const T* y = Y + ((l * I) * Q + q) * R + r;
+    const T* a = A + r;
     const int64_t stride = Q * R;
     double acc = 0.0;
-    for (int i = 0; i < I; ++i) acc += (double)y[i * stride] * (double)A[(size_t)i * R + r];
+    int i = 0;
+    if (sizeof(T) == 4) {
+      // fp32 data: eight products per fp32 partial (eight independent loads in flight), partials summed in fp64 — the
+      // fp64 pipe (16 lanes/clk/SM on B200) would otherwise cap this kernel below HBM speed
+      for (; i + 8 <= I; i += 8) {
+        float part = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part = fmaf((float)y[(int64_t)(i + u) * stride], (float)a[(size_t)(i + u) * R], part);
+        acc += (double)part;
+      }
+    }
+    for (; i < I; ++i) acc += (double)y[(int64_t)i * stride] * (double)a[(size_t)i * R];
     out[idx] = (T)acc;
   }
 }
@@ -172,6 +184,92 @@ inline int cp_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, T* 
   return TNB_OK;
 }
 
+// out[c, r] = in[r, c]   (in: rows x cols row-major).  32 x 32 tiles through shared memory, both sides coalesced.
+template <typename T>
+__global__ void cp_transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t cols) {
+  __shared__ T tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  for (int64_t c0 = (int64_t)blockIdx.y * 32; c0 < cols; c0 += (int64_t)gridDim.y * 32) {
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int64_t r = r0 + j, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int64_t c = c0 + j, r = r0 + threadIdx.x;
+      if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+    }
+    __syncthreads();
+  }
+}
+
+// One ALS sweep's MTTKRPs as a dimension tree (N >= 3).  Within a sweep the factors of modes > n are still the old ones
+// when mode n is updated, so
+//   * Y = X x_{N-1} A_{N-1} (ONE pass over X) serves modes 0..N-2, and the right-to-left chain
+//     R_k = R_{k+1} x_{k+1} A_{k+1} (R_{N-2} = Y, alive modes [0, k]) is built once; M_n = R_n reduced over modes < n
+//     with the freshly updated factors;
+//   * mode N-1 contracts the last mode of XT (X with mode N-1 moved to the front, transposed once per call) with
+//     A_{N-2} through the same projection kernel and reduces modes N-3..0 — instead of a first-mode (strided) GEMM.
+// Per sweep X is read twice (not N times); the reference recomputes the full Khatri-Rao product and a permuted copy of
+// X for every mode (tensor.py:351-357).
+template <typename T>
+struct CpTree {
+  T* Yk = nullptr;      // max(numel / I_{N-1}, numel / I_{N-2}) * R
+  T* T0 = nullptr;      // reduction ping-pong
+  T* T1 = nullptr;
+  T* XT = nullptr;      // numel
+  std::vector<T*> chain;  // chain[k], k = 0..N-3: prod_{m<=k} I_m * R
+};
+
+template <typename T>
+inline void cp_khatri(const T* Y, const T* A, T* out, int64_t L, int64_t I, int64_t Q, int R, cudaStream_t st) {
+  khatri_reduce_kernel<T><<<grid_for(L * Q * R, 256, 8192), 256, 0, st>>>(Y, A, out, L, (int)I, Q, R);
+}
+
+template <typename T>
+inline int cp_tree_mttkrp(const T* X, const CpDims& d, int n, int R, T* const* A, CpTree<T>& tr, T* Mout, cudaStream_t st,
+                          void* tc_ws, size_t tc_ws_bytes) {
+  const int N = d.N;
+  if (n == 0) {
+    TNB_TRY(project_any<T>(X, d.numel / d.shape[N - 1], d.shape[N - 1], A[N - 1], R, tr.Yk, st, tc_ws, tc_ws_bytes));
+    const T* src = tr.Yk;
+    for (int k = N - 3; k >= 0; --k) {  // R_k = R_{k+1} x_{k+1} A_{k+1}
+      cp_khatri<T>(src, A[k + 1], tr.chain[k], d.left[k + 1], d.shape[k + 1], 1, R, st);
+      TNB_LAUNCH_CHECK();
+      src = tr.chain[k];
+    }
+    TNB_CUDA(cudaMemcpyAsync(Mout, tr.chain[0], sizeof(T) * (size_t)d.shape[0] * R, cudaMemcpyDeviceToDevice, st));
+    return TNB_OK;
+  }
+  const T* cur;
+  T* bufs[2] = {tr.T0, tr.T1};
+  int flip = 0;
+  if (n <= N - 2) {
+    cur = (n == N - 2) ? tr.Yk : tr.chain[n];  // alive modes [0, n]
+    for (int lo = 0; lo < n; ++lo) {
+      int64_t Q = 1;
+      for (int m = lo + 1; m <= n; ++m) Q *= d.shape[m];
+      T* dst = (lo + 1 == n) ? Mout : bufs[flip];
+      cp_khatri<T>(cur, A[lo], dst, 1, d.shape[lo], Q, R, st);
+      TNB_LAUNCH_CHECK();
+      cur = dst;
+      flip ^= 1;
+    }
+    return TNB_OK;
+  }
+  // n == N-1: XT is [I_{N-1}, I_0, ..., I_{N-2}]
+  TNB_TRY(project_any<T>(tr.XT, d.numel / d.shape[N - 2], d.shape[N - 2], A[N - 2], R, tr.Yk, st, tc_ws, tc_ws_bytes));
+  cur = tr.Yk;
+  for (int m = N - 3; m >= 0; --m) {
+    T* dst = (m == 0) ? Mout : bufs[flip];
+    cp_khatri<T>(cur, A[m], dst, d.shape[N - 1] * d.left[m], d.shape[m], 1, R, st);
+    TNB_LAUNCH_CHECK();
+    cur = dst;
+    flip ^= 1;
+  }
+  return TNB_OK;
+}
+
 // acc[0] += sum x^2 (fp64)
 template <typename T>
 __global__ void cp_sumsq_kernel(const T* __restrict__ X, int64_t n, double* __restrict__ acc) {
@@ -194,8 +292,8 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
   int64_t imax = 0;
   for (int n = 0; n < N; ++n) imax = std::max<int64_t>(imax, d.shape[n]);
   const int64_t ymax = d.numel / std::min<int64_t>(d.shape[0], d.shape[N - 1]) * R;
-  T* Y0 = ar.template take<T>(ymax);
-  T* Y1 = ar.template take<T>(ymax / std::min<int64_t>(d.shape[N > 2 ? N - 2 : 0], d.shape[N > 2 ? 1 : 0]) + 64);
+  T* Y0 = ar.template take<T>(N == 2 ? ymax : 64);  // the plain two-GEMM path of N == 2
+  T* Y1 = ar.template take<T>(N == 2 ? ymax + 64 : 64);
   T* Mbuf = ar.template take<T>(imax * R);
   T* Anew = ar.template take<T>(imax * R);
   double* grams = ar.template take<double>((size_t)N * R * R);
@@ -211,9 +309,22 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
   double* gpart = ar.template take<double>(plg.partial_elems + 64);
   void* ptc_ws = nullptr;
   size_t ptc_bytes = 0;
-  if (std::is_same<T, float>::value && R <= PT_MAX_N && d.shape[N - 1] % 4 == 0 && d.shape[N - 1] >= 32) {
-    ptc_bytes = project_tc_workspace_bytes(d.shape[N - 1], R);
-    ptc_ws = ar.template take<char>(ptc_bytes);
+  const bool tree = N >= 3;  // dimension-tree sweeps (cp_tree_mttkrp); N == 2 keeps the two plain GEMMs
+  for (int m = tree ? N - 2 : N - 1; m < N; ++m)
+    if (std::is_same<T, float>::value && R <= PT_MAX_N && d.shape[m] % 4 == 0 && d.shape[m] >= 32)
+      ptc_bytes = std::max(ptc_bytes, project_tc_workspace_bytes(d.shape[m], R));
+  if (ptc_bytes) ptc_ws = ar.template take<char>(ptc_bytes);
+  CpTree<T> tr;
+  if (tree) {
+    int64_t imin = d.shape[0];
+    for (int n = 1; n < N; ++n) imin = std::min<int64_t>(imin, d.shape[n]);
+    const int64_t yk = d.numel / std::min<int64_t>(d.shape[N - 1], d.shape[N - 2]) * R;
+    tr.Yk = ar.template take<T>(yk);
+    tr.T0 = ar.template take<T>(yk / imin + 64);
+    tr.T1 = ar.template take<T>(yk / imin + 64);
+    tr.XT = ar.template take<T>(d.numel);
+    tr.chain.resize(N - 2);
+    for (int k = 0; k <= N - 3; ++k) tr.chain[k] = ar.template take<T>(d.left[k + 1] * R + 64);
   }
   // HOSVD init scratch: mode Gram (I x I) + eigen workspace, sized for the largest mode
   size_t peak = ar.off;
@@ -304,11 +415,20 @@ inline int cp_als_impl(ArenaT& ar, bool dry, const T* X, const CpDims& d, int R,
   }
 
   // ---------------- ALS sweeps (tensor.py:323-400) ----------------
+  if (tree) {  // XT[i_{N-1}, rest] = X[rest, i_{N-1}], once per call
+    const int64_t rows = d.numel / d.shape[N - 1], cols = d.shape[N - 1];
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)std::min<int64_t>((cols + 31) / 32, 65535));
+    cp_transpose_kernel<T><<<grid, dim3(32, 8), 0, st>>>(X, tr.XT, rows, cols);
+    TNB_LAUNCH_CHECK();
+  }
   int it = 0;
   double prev_err = 0.0;
   for (; it < max_iter; ++it) {
     for (int n = 0; n < N; ++n) {
-      TNB_TRY(cp_mttkrp<T>(X, d, n, R, A.data(), Y0, Y1, Mbuf, st, ptc_ws, ptc_bytes));
+      if (tree)
+        TNB_TRY(cp_tree_mttkrp<T>(X, d, n, R, A.data(), tr, Mbuf, st, ptc_ws, ptc_bytes));
+      else
+        TNB_TRY(cp_mttkrp<T>(X, d, n, R, A.data(), Y0, Y1, Mbuf, st, ptc_ws, ptc_bytes));
       hadamard_grams_kernel<<<grid_for(R * R), 256, 0, st>>>(gp, N, n, R, P);
       TNB_LAUNCH_CHECK();
       if (n == N - 1) {  // <X, [[A]]> needs M_{N-1} and the NEW A_{N-1}; ||[[A]]||^2 needs all new grams
