@@ -67,7 +67,7 @@ __device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t 
 }
 
 // KC rows of C per pipeline stage (32: 4 KB TMA boxes, 6 stages; 64: 8 KB boxes, 3 stages — half as many TMA instructions
-// and barrier round trips per byte; A/B switch TNB_TC2_KC, profiles/r02_ncu_summaries.md)
+// and barrier round trips per byte for the single producer / issuer threads; A/B in profiles/r02_gram_tc2_depth.md)
 template <int KC, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gram_tc2_kernel_t(const __grid_constant__ CUtensorMap tmap, const GramTc2Params p) {
@@ -209,7 +209,8 @@ __global__ void gram_tc2_finalize_kernel(const GramTc2Params p, double* __restri
 inline bool gram_tc2_shape_ok(int64_t rows, int64_t n) { return n >= 512 && gram_tc_shape_ok(rows, n); }
 
 inline int gram_tc2_kc() {
-  static const int kc = (getenv("TNB_TC2_KC") && atoi(getenv("TNB_TC2_KC")) == 64) ? 64 : 32;
+  // 64 measured 21 % faster than 32 on the 262144 x 2048 Gram (profiles/r02_gram_tc2_depth.md); TNB_TC2_KC=32 switches back
+  static const int kc = (getenv("TNB_TC2_KC") && atoi(getenv("TNB_TC2_KC")) == 32) ? 32 : 64;
   return kc;
 }
 inline void gram_tc2_plan(int64_t rows, int64_t n, GramTc2Params& p) {
