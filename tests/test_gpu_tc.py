@@ -68,7 +68,9 @@ def test_atb_tc_matches_fp64(shape):
     assert torch.equal(Ci.double(), Ai.double().T @ Bi.double())
 
 
-@pytest.mark.parametrize("shape", [(16384, 64, 32), (20000, 2048, 32), (4096 + 77, 96, 17), (70000, 64, 64), (1000, 32, 8)])
+@pytest.mark.parametrize("shape", [(16384, 64, 32), (20000, 2048, 32), (4096 + 77, 96, 17), (70000, 64, 64), (1000, 32, 8),
+                                   # V resident beyond 32 KB: stages handed back by the split warps (CP-ALS projections)
+                                   (300000 + 5, 256, 50), (40000, 128, 64), (50000, 512, 32), (33000, 256, 64)])
 def test_project_tc_fp32_accuracy(shape):
     """3xTF32 projection on the tensor cores keeps fp32 accuracy (a 1xTF32 product would be ~2^-11)."""
     from tntorch_b200 import ops

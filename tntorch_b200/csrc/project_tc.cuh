@@ -50,6 +50,9 @@ struct ProjTcParams {
                // into slabs of PT_SLAB_CHUNKS*32 columns whose partial tiles are summed in fp32 (RN) by the epilogue
   int nslabs;
   int vres;         // 1: all V chunks resident in shared memory (small K), stages hold A only
+  int early;        // 1 (vres only): an A stage is handed back by the four split warps as soon as they have read it, not by
+                    // the MMA commit — the stage ring then only has to cover the TMA latency, which is what makes a
+                    // 4-stage ring next to 128 KB of resident V (K = 256, r <= 64: the CP-ALS projections) viable
   int stage_bytes;  // 16 KB (+ 2*npad*128 B of V chunk when streaming V)
   int nstages;      // ring depth that fits PT_RING_BYTES: the HBM latency needs >= ~140 KB in flight per SM
   int alo_slots;    // A_lo ring depth in use (<= PT_ALO_SLOTS)
@@ -129,7 +132,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < PT_MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.early ? 4 : 1);
     }
     for (int s = 0; s < PT_ALO_SLOTS; ++s) {
       mbar_init(&alo_full[s], 4);    // one arrival per split warp
@@ -207,7 +210,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t vb = p.vres ? vres0 + (uint32_t)(kc * vchunk_bytes) : sb + PT_A_BYTES;
           const uint64_t bd = desc_hi | (uint64_t)((vb >> 4) & 0x3FFF);
           const uint32_t araw = tmem_base + (uint32_t)(PT_ALO_COL + aslot * PT_ALO_W), alo = araw + PT_KC;
-          mbar_wait(&full_bar[stage], phase);   // V chunk of this stage (streaming mode) landed
+          if (!p.early) mbar_wait(&full_bar[stage], phase);   // V chunk of this stage (streaming mode) landed
           mbar_wait(&alo_full[aslot], aphase);  // the split warps have put A (raw) and A_lo of this chunk in tensor memory
           tcgen05_fence_after();
           // A_hi (raw bits, truncated by the tensor core) x [V_hi; V_lo]; one k-step = 8 TMEM columns / 32 B of V
@@ -219,7 +222,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tcgen05_mma_tf32_ts(tmem_d, alo + 8, bd + 2, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 16, bd + 4, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 24, bd + 6, idesc1, 1u);
-          tcgen05_commit(&empty_bar[stage]);   // shared-memory stage reusable
+          if (!p.early) tcgen05_commit(&empty_bar[stage]);   // shared-memory stage reusable
           tcgen05_commit(&alo_empty[aslot]);   // tensor-memory A_lo slot reusable
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
           if (++aslot == p.alo_slots) { aslot = 0; aphase ^= 1u; }
@@ -251,6 +254,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         lo[4 * u + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
         lo[4 * u + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
         lo[4 * u + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+      }
+      if (p.early) {  // the row is in registers: the stage can be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
       }
       mbar_wait(&alo_empty[aslot], aphase ^ 1u);  // the MMAs that read this slot last have completed
       tcgen05_fence_after();
@@ -375,7 +382,13 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   p.nslabs = (p.nk + p.slab - 1) / p.slab;
   p.C = C;
   const int vchunk = 2 * p.npad * PT_KC * 4;
-  p.vres = ((int64_t)p.nk * vchunk <= PT_VRES_MAX_BYTES) ? 1 : 0;
+  // A/B switches: TNB_PT_VRES_KB (largest resident V, default 128; 32 = the round-1 rule), TNB_PT_EARLY (0 / 1 forces the
+  // stage hand-back rule; default: early only when V is larger than the round-1 limit)
+  static const int vres_kb = getenv("TNB_PT_VRES_KB") ? atoi(getenv("TNB_PT_VRES_KB")) : 128;
+  static const int early_env = getenv("TNB_PT_EARLY") ? atoi(getenv("TNB_PT_EARLY")) : -1;
+  const int64_t vbytes = (int64_t)p.nk * vchunk;
+  p.vres = (vbytes <= (int64_t)vres_kb * 1024 && vbytes <= PT_RING_BYTES - 4 * PT_A_BYTES) ? 1 : 0;
+  p.early = p.vres && (early_env >= 0 ? early_env : (vbytes > PT_VRES_MAX_BYTES ? 1 : 0));
   p.stage_bytes = PT_A_BYTES + (p.vres ? 0 : vchunk);
   p.nstages = (PT_RING_BYTES - (p.vres ? p.nk * vchunk : 0)) / p.stage_bytes;
   if (p.nstages > PT_MAX_STAGES) p.nstages = PT_MAX_STAGES;
