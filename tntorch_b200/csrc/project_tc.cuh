@@ -30,7 +30,8 @@ constexpr int PT_BM = 128, PT_KC = 32, PT_MAX_STAGES = 12, PT_THREADS = 320;
 constexpr int PT_A_BYTES = PT_BM * PT_KC * 4;      // 16 KB
 constexpr int PT_MAX_N = 64;                        // r padded to a multiple of 16, <= 64
 constexpr int PT_RING_BYTES = 192 * 1024;           // stage ring (+ resident V when it fits)
-constexpr int PT_SMEM_BYTES = PT_RING_BYTES + 1024 + 512;
+constexpr int PT_EPI_BYTES = 4 * 32 * 64 * 4;        // per epilogue warp: 32 rows x <= 64 columns, staged for coalesced stores
+constexpr int PT_SMEM_BYTES = PT_RING_BYTES + 1024 + 512 + PT_EPI_BYTES;
 constexpr int PT_VRES_MAX_BYTES = 32 * 1024;        // V_hi|V_lo kept in shared memory for the whole kernel up to this size
 constexpr int PT_ACC_COLS = 256;                    // accumulator slots: 256 / (2*npad) of width 2*npad
 constexpr int PT_ALO_COL = PT_ACC_COLS;             // A_lo ring: PT_ALO_SLOTS x 32 columns behind the accumulators
@@ -50,9 +51,6 @@ struct ProjTcParams {
                // into slabs of PT_SLAB_CHUNKS*32 columns whose partial tiles are summed in fp32 (RN) by the epilogue
   int nslabs;
   int vres;         // 1: all V chunks resident in shared memory (small K), stages hold A only
-  int early;        // 1 (vres only): an A stage is handed back by the four split warps as soon as they have read it, not by
-                    // the MMA commit — the stage ring then only has to cover the TMA latency, which is what makes a
-                    // 4-stage ring next to 128 KB of resident V (K = 256, r <= 64: the CP-ALS projections) viable
   int stage_bytes;  // 16 KB (+ 2*npad*128 B of V chunk when streaming V)
   int nstages;      // ring depth that fits PT_RING_BYTES: the HBM latency needs >= ~140 KB in flight per SM
   int alo_slots;    // A_lo ring depth in use (<= PT_ALO_SLOTS)
@@ -132,7 +130,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < PT_MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], p.early ? 4 : 1);
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < PT_ALO_SLOTS; ++s) {
       mbar_init(&alo_full[s], 4);    // one arrival per split warp
@@ -210,7 +208,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t vb = p.vres ? vres0 + (uint32_t)(kc * vchunk_bytes) : sb + PT_A_BYTES;
           const uint64_t bd = desc_hi | (uint64_t)((vb >> 4) & 0x3FFF);
           const uint32_t araw = tmem_base + (uint32_t)(PT_ALO_COL + aslot * PT_ALO_W), alo = araw + PT_KC;
-          if (!p.early) mbar_wait(&full_bar[stage], phase);   // V chunk of this stage (streaming mode) landed
+          mbar_wait(&full_bar[stage], phase);   // V chunk of this stage (streaming mode) landed
           mbar_wait(&alo_full[aslot], aphase);  // the split warps have put A (raw) and A_lo of this chunk in tensor memory
           tcgen05_fence_after();
           // A_hi (raw bits, truncated by the tensor core) x [V_hi; V_lo]; one k-step = 8 TMEM columns / 32 B of V
@@ -222,7 +220,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tcgen05_mma_tf32_ts(tmem_d, alo + 8, bd + 2, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 16, bd + 4, idesc1, 1u);
           tcgen05_mma_tf32_ts(tmem_d, alo + 24, bd + 6, idesc1, 1u);
-          if (!p.early) tcgen05_commit(&empty_bar[stage]);   // shared-memory stage reusable
+          tcgen05_commit(&empty_bar[stage]);   // shared-memory stage reusable
           tcgen05_commit(&alo_empty[aslot]);   // tensor-memory A_lo slot reusable
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
           if (++aslot == p.alo_slots) { aslot = 0; aphase ^= 1u; }
@@ -255,10 +253,6 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         lo[4 * u + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
         lo[4 * u + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
       }
-      if (p.early) {  // the row is in registers: the stage can be refilled
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      }
       mbar_wait(&alo_empty[aslot], aphase ^ 1u);  // the MMAs that read this slot last have completed
       tcgen05_fence_after();
       const uint32_t tdst = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(PT_ALO_COL + aslot * PT_ALO_W);
@@ -275,6 +269,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ================= epilogue warps =================
     const int lane_group = warp_idx & 3;
     const int row_in_tile = lane_group * 32 + lane;
+    float* epi = reinterpret_cast<float*>(stage_base + PT_RING_BYTES + 512) + (size_t)lane_group * 32 * 64;
     const int64_t tiles = my_blocks * p.nslabs;
     int slot = 0, sl = 0;
     uint32_t acc_phase = 0;
@@ -283,15 +278,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool add = sl != 0;  // later slabs of a row block add to what this warp stored before
       mbar_wait(&acc_full[slot], acc_phase);
       tcgen05_fence_after();
-      for (int c0 = 0; c0 < p.npad; c0 += 16) {
-        uint32_t v[16], w[16];
-        const uint32_t t0 = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(slot * slot_w + c0);
-        tmem_ld_32x32b_x16(t0, v);                       // A_hi V_hi + A_lo V_hi
-        tmem_ld_32x32b_x16(t0 + (uint32_t)p.npad, w);    // A_hi V_lo
-        tmem_ld_wait();
-        if (grow < p.rows) {
-          float* out = p.C + grow * p.r + c0;
-          if ((p.r & 3) == 0) {
+      if ((p.r & 3) == 0) {
+        // r a multiple of 4 (the TT sweep): every lane stores its own row in 16-byte pieces
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+          uint32_t v[16], w[16];
+          const uint32_t t0 = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(slot * slot_w + c0);
+          tmem_ld_32x32b_x16(t0, v);                       // A_hi V_hi + A_lo V_hi
+          tmem_ld_32x32b_x16(t0 + (uint32_t)p.npad, w);    // A_hi V_lo
+          tmem_ld_wait();
+          if (grow < p.rows) {
+            float* out = p.C + grow * p.r + c0;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (c0 + 4 * q + 3 < p.r) {
@@ -306,19 +302,49 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 *dst = o;
               }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (c0 + q < p.r) {
-                const float x = __uint_as_float(v[q]) + __uint_as_float(w[q]);
-                out[q] = add ? out[q] + x : x;
-              }
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      } else {
+        // Any other r (the CP-ALS projections, r = 50): a lane storing its own row would write 4-byte pieces into 32
+        // different sectors per instruction.  The 32 rows of this warp are ONE contiguous block of 32*r floats of C, so
+        // the tile goes through shared memory (row-major, stride r) and leaves as full 128-byte lines.
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+          uint32_t v[16], w[16];
+          const uint32_t t0 = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(slot * slot_w + c0);
+          tmem_ld_32x32b_x16(t0, v);
+          tmem_ld_32x32b_x16(t0 + (uint32_t)p.npad, w);
+          tmem_ld_wait();
+          float* srow = epi + lane * p.r + c0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (c0 + q < p.r) srow[q] = __uint_as_float(v[q]) + __uint_as_float(w[q]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);  // the accumulator is free while the tile drains from shared memory
+        const int64_t wrow0 = grow - lane;  // first row of this warp's block
+        int64_t nvalid = p.rows - wrow0;
+        if (nvalid > 32) nvalid = 32;
+        if (nvalid > 0) {
+          float* gout = p.C + wrow0 * p.r;  // 32*r*4 bytes per warp block, 128*r*4 per tile: 16-byte aligned
+          const int nfl = (int)nvalid * p.r, n4 = nfl >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(epi);
+          float4* g4 = reinterpret_cast<float4*>(gout);
+          for (int i = lane; i < n4; i += 32) {
+            float4 o = s4[i];
+            if (add) {
+              const float4 old = g4[i];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            g4[i] = o;
+          }
+          for (int i = 4 * n4 + lane; i < nfl; i += 32) gout[i] = add ? gout[i] + epi[i] : epi[i];
+        }
+        __syncwarp();  // the staging block is rewritten by the next tile
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[slot]);
       if (++slot == nslots) { slot = 0; acc_phase ^= 1u; }
       if (++sl == p.nslabs) { sl = 0; grow += (int64_t)gridDim.x * PT_BM; }
     }
@@ -382,13 +408,7 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   p.nslabs = (p.nk + p.slab - 1) / p.slab;
   p.C = C;
   const int vchunk = 2 * p.npad * PT_KC * 4;
-  // A/B switches: TNB_PT_VRES_KB (largest resident V, default 128; 32 = the round-1 rule), TNB_PT_EARLY (0 / 1 forces the
-  // stage hand-back rule; default: early only when V is larger than the round-1 limit)
-  static const int vres_kb = getenv("TNB_PT_VRES_KB") ? atoi(getenv("TNB_PT_VRES_KB")) : 128;
-  static const int early_env = getenv("TNB_PT_EARLY") ? atoi(getenv("TNB_PT_EARLY")) : -1;
-  const int64_t vbytes = (int64_t)p.nk * vchunk;
-  p.vres = (vbytes <= (int64_t)vres_kb * 1024 && vbytes <= PT_RING_BYTES - 4 * PT_A_BYTES) ? 1 : 0;
-  p.early = p.vres && (early_env >= 0 ? early_env : (vbytes > PT_VRES_MAX_BYTES ? 1 : 0));
+  p.vres = ((int64_t)p.nk * vchunk <= PT_VRES_MAX_BYTES) ? 1 : 0;
   p.stage_bytes = PT_A_BYTES + (p.vres ? 0 : vchunk);
   p.nstages = (PT_RING_BYTES - (p.vres ? p.nk * vchunk : 0)) / p.stage_bytes;
   if (p.nstages > PT_MAX_STAGES) p.nstages = PT_MAX_STAGES;
@@ -405,7 +425,8 @@ inline int project_tc_f32(const float* A, int64_t rows, int64_t K, const float* 
   TNB_CUDA(ensure_dyn_smem(attr_done, project_tc_kernel, PT_SMEM_BYTES));
   const int sms = usable_sms();
   const int64_t grid = p.num_row_blocks < sms ? p.num_row_blocks : sms;
-  project_tc_kernel<<<(unsigned)grid, PT_THREADS, PT_SMEM_BYTES, st>>>(ta, th, tl, p);
+  const int smem = PT_SMEM_BYTES - ((r & 3) == 0 ? PT_EPI_BYTES : 0);  // the staging block only where it is used
+  project_tc_kernel<<<(unsigned)grid, PT_THREADS, smem, st>>>(ta, th, tl, p);
   TNB_LAUNCH_CHECK();
   return TNB_OK;
 }
