@@ -83,6 +83,36 @@ __global__ void __launch_bounds__(256) khatri_reduce2_kernel(const float* __rest
   }
 }
 
+// Few outputs (the inner steps of a chain: L*Q*R/2 of a few thousand): eight lanes share one output pair, each summing
+// every eighth row, so that the I rows are not walked by one thread alone (80 us -> latency of I/8 rows).
+__global__ void __launch_bounds__(256) khatri_reduce2_split_kernel(const float* __restrict__ Y, const float* __restrict__ A,
+                                                                   float* __restrict__ out, int64_t L, int I, int64_t Q,
+                                                                   int R) {
+  const int R2 = R >> 1;
+  const int64_t total = L * Q * R2;
+  const int g = threadIdx.x & 7;
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  double acc0 = 0.0, acc1 = 0.0;
+  if (idx < total) {
+    const int rv = (int)(idx % R2);
+    const int64_t q = (idx / R2) % Q, l = idx / ((int64_t)R2 * Q);
+    const float2* y = reinterpret_cast<const float2*>(Y + ((l * I) * Q + q) * R) + rv;
+    const float2* a = reinterpret_cast<const float2*>(A) + rv;
+    const int64_t stride = Q * R2;
+#pragma unroll 4
+    for (int i = g; i < I; i += 8) {
+      const float2 yv = y[(int64_t)i * stride], av = __ldg(a + (size_t)i * R2);
+      acc0 += (double)yv.x * (double)av.x;
+      acc1 += (double)yv.y * (double)av.y;
+    }
+  }
+  for (int o = 4; o > 0; o >>= 1) {  // the eight lanes of a group are adjacent lanes of one warp
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+  }
+  if (g == 0 && idx < total) reinterpret_cast<float2*>(out)[idx] = make_float2((float)acc0, (float)acc1);
+}
+
 struct GramPtrs {
   const double* g[16];
 };
@@ -263,6 +293,12 @@ struct CpTree {
 template <typename T>
 inline void cp_khatri(const T* Y, const T* A, T* out, int64_t L, int64_t I, int64_t Q, int R, cudaStream_t st) {
   const bool al8 = ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(out)) & 7u) == 0;
+  if (std::is_same<T, float>::value && (R & 1) == 0 && al8 && L * Q * (R / 2) < 148 * 256) {
+    const int64_t threads = L * Q * (R / 2) * 8;
+    khatri_reduce2_split_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float*>(Y), reinterpret_cast<const float*>(A), reinterpret_cast<float*>(out), L, (int)I, Q, R);
+    return;
+  }
   if (std::is_same<T, float>::value && (R & 1) == 0 && al8) {
     khatri_reduce2_kernel<<<grid_for(L * Q * (R / 2), 256, 16384), 256, 0, st>>>(
         reinterpret_cast<const float*>(Y), reinterpret_cast<const float*>(A), reinterpret_cast<float*>(out), L, (int)I, Q, R);
