@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(1024) jacobi2_eigh_kernel(const double* __rest
   __shared__ int s_sweeps;
   Jac2<R> J;
   jac2_carve<R>(jac2_smem, n, tol, J);
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int np = J.np, lds = J.lds;
   double dmax = 0.0;
   for (int i = tid; i < n; i += nt) dmax = fmax(dmax, fabs(Gin[(size_t)i * ldg + i]));
