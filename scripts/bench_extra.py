@@ -46,9 +46,9 @@ if "cfg4" in which:  # CP-ALS R=50 on a synthetic rank-50 256^4 (16 GiB fp32); a
         fi = ops.cp_als(X, 50, max_iter=sweeps, tol=float("-inf"), return_info=True)
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / 1e3, fi[1]
-    d1, _ = timed(1)
-    dt, info = timed(5)
-    out["cfg4_cp_als_256^4_R50_f32"] = {"s_per_sweep": (dt - d1) / 4, "init_plus_1_sweep_s": d1, "five_sweeps_s": dt, "errors": info["errors"]}
+    d1 = min(timed(1)[0] for _ in range(3))  # the HOSVD initialisation (1.1 s) dominates both: take the fastest of 3
+    dt, info = min((timed(21) for _ in range(3)), key=lambda t: t[0])
+    out["cfg4_cp_als_256^4_R50_f32"] = {"s_per_sweep": (dt - d1) / 20, "init_plus_1_sweep_s": d1, "21_sweeps_s": dt, "errors": info["errors"][:5]}
     print(json.dumps(out), flush=True)
     del X
 if "cfg5" in which:  # TT-cross 32^6, ranks 10, 3 sweeps (the unit of BASELINE configs[4]); sequential problems
