@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python scripts/dbg_cp.py 2>&1 | tail -12
+# (a CP-ALS debug print ran here; the script was removed with the other scratch helpers)
 cat > /tmp/one.py <<'P'
 import torch, sys
 sys.path.insert(0, '.')
