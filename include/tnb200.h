@@ -209,6 +209,9 @@ int tnb_truncated_svd(int dtype, const void* M, int64_t m, int64_t n, double del
  *                capacity from tnb_cp_als_factors_capacity()
  *   errors_host  max_iter doubles: relative error after each sweep;  *iters_host: sweeps performed
  *   tol          stop when errors[-2] - errors[-1] < tol (pass -INFINITY for a fixed sweep count)
+ *   workspace    for ndim >= 3 it holds one permuted copy of the data (mode ndim-1 moved to the front, numel elements)
+ *                plus one numel / min(shape[ndim-1], shape[ndim-2]) * R intermediate: every sweep reads the data twice
+ *                (one projection shared by modes 0..ndim-2, one over the permuted copy for the last mode)
  * ------------------------------------------------------------------------------------------ */
 int64_t tnb_cp_als_factors_capacity(int ndim, const int64_t* shape, int32_t R, int64_t* factor_offsets_host);
 size_t tnb_cp_als_workspace_bytes(int dtype, int ndim, const int64_t* shape, int32_t R);
